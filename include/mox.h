@@ -1,0 +1,193 @@
+/* mox.h — the C ABI of the B200-native render path.
+ *
+ * This is the drop-in boundary: everything MinimalOptiX does through the OptiX 5.1
+ * host API (optixpp Context / Geometry / Material / GeometryInstance / Group /
+ * Acceleration / Buffer / launch and the named rtVariables) is reachable through
+ * the entry points below, with plain pointers and sizes only.  Each entry point
+ * cites the reference call(s) it replaces (paths relative to
+ * /root/reference/MinimalOptiX/).
+ *
+ * Conventions
+ *  - every function returns MOX_OK (0) or a negative mox_status; the text of the
+ *    last failure is available from mox_last_error().  No C++ exception crosses
+ *    the ABI.  (The reference lets optix::Exception / std::logic_error kill the
+ *    process, MinimalOptiX.cpp:388,512.)
+ *  - all host inputs are copied before the call returns (the reference memcpy()s
+ *    into map()ped buffers and setUserData() copies, MinimalOptiX.cpp:398,528).
+ *  - a context is not thread-safe; different contexts may be used concurrently.
+ *  - mox_launch / mox_render / mox_trace_* are synchronous on return.
+ *  - primitive ids are global and dense in insertion order over all mox_add_*
+ *    calls (mesh faces in face order).
+ *  - there is NO CPU fallback: every compute entry point fails with
+ *    MOX_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef MOX_H
+#define MOX_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "mox_structs.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOX_ABI_VERSION 1
+
+typedef struct mox_ctx mox_ctx; /* opaque */
+
+typedef enum mox_status {
+  MOX_OK = 0,
+  MOX_ERR_INVALID = -1,   /* bad argument / call order */
+  MOX_ERR_CUDA = -2,      /* CUDA runtime failure or no usable device */
+  MOX_ERR_OOM = -3,       /* device or host allocation failed */
+  MOX_ERR_STATE = -4      /* e.g. launch before mox_build_accel */
+} mox_status;
+
+/* Which closest-hit program a primitive runs (Material.cu:28,49,72,118,238). */
+typedef enum mox_material_kind {
+  MOX_MAT_LAMBERTIAN = 0, /* params: LambertianParams */
+  MOX_MAT_METAL = 1,      /* params: MetalParams      */
+  MOX_MAT_GLASS = 2,      /* params: GlassParams      */
+  MOX_MAT_DISNEY = 3,     /* params: DisneyParams     */
+  MOX_MAT_LIGHT = 4       /* params: LightParams (only .emission is read) */
+} mox_material_kind;
+
+/* Per-path random numbers.  REF reproduces the reference stream exactly
+ * (tea<16> seeding + 24-bit LCG, utils_device.h:8-34); PHILOX is Philox4x32-10
+ * keyed by (pixel, launch seed) with the draw index as counter. */
+typedef enum mox_rng_mode { MOX_RNG_REF = 0, MOX_RNG_PHILOX = 1 } mox_rng_mode;
+
+/* mox_build_accel flags */
+#define MOX_ACCEL_DEFAULT 0u
+#define MOX_ACCEL_BVH2 1u        /* keep the binary LBVH (debug / comparison)     */
+#define MOX_ACCEL_COUNTERS 2u    /* traversal kernels count node visits / prim tests */
+
+typedef struct mox_stats {
+  uint64_t rays_primary;      /* camera rays traced (closest hit)                 */
+  uint64_t rays_bounce;       /* scattered rays traced (closest hit)              */
+  uint64_t rays_shadow;       /* NEE shadow rays traced (any hit)                 */
+  uint64_t nonfinite_samples; /* samples that were NaN/Inf before the clamp       */
+  uint64_t launches;          /* launches since the last clear                    */
+  uint64_t node_visits;       /* only with MOX_ACCEL_COUNTERS                     */
+  uint64_t prim_tests;        /* only with MOX_ACCEL_COUNTERS                     */
+  double ms_render;           /* device time in launch/render since last clear    */
+  double ms_build;            /* device time of the last mox_build_accel          */
+  uint32_t n_prims, n_triangles, n_spheres, n_quads;
+  uint32_t n_nodes;           /* nodes of the acceleration structure traversed    */
+  uint32_t node_bytes;        /* bytes per node record                            */
+  uint32_t prim_bytes;        /* bytes per packed triangle record                 */
+  uint32_t n_lights;
+} mox_stats;
+
+/* ---- context ------------------------------------------------------------- */
+
+/* Context::create + setRayTypeCount(2)/setEntryPointCount(1)
+ * (MinimalOptiX.cpp:130-134).  device_id is the CUDA ordinal of the ONE GPU this
+ * context renders on; multi-GPU runs use one context per GPU (one process per
+ * GPU) with mox_set_partition. */
+int mox_create(mox_ctx** out, int device_id);
+void mox_destroy(mox_ctx*);
+const char* mox_last_error(const mox_ctx*); /* ctx may be NULL: last create error */
+int mox_abi_version(void);
+
+/* The context-level rtVariables rayMaxDepth, rayEpsilonT, rayMinIntensity,
+ * absorbColor, badColor (MinimalOptiX.cpp:136-151), the miss program's bgColor
+ * (:163-165) and the launch size / accuBuffer dimensions (:144-147, :546).
+ * (Re)allocates and zeroes the accumulation buffer when the size changes. */
+int mox_set_globals(mox_ctx*, uint32_t width, uint32_t height, uint32_t rayMaxDepth,
+                    float rayEpsilonT, float rayMinIntensity, const float absorbColor[3],
+                    const float badColor[3], const float bgColor[3]);
+
+/* rayGenProgram["camParams"]->setUserData (MinimalOptiX.cpp:255). */
+int mox_set_camera(mox_ctx*, const CamParams*);
+
+int mox_set_rng_mode(mox_ctx*, int mode /* mox_rng_mode */);
+
+/* Tile split for multi-GPU: the image is cut into tile x tile pixel squares and
+ * this context renders those with (tx + ty) % world == rank.  Seeds depend only
+ * on the global pixel index, so the union over ranks equals the 1-rank image
+ * bit for bit.  Default: rank 0 of world 1 (whole image), tile 32. */
+int mox_set_partition(mox_ctx*, uint32_t rank, uint32_t world, uint32_t tile);
+
+/* ---- scene --------------------------------------------------------------- */
+
+/* createTextureSampler + float4 buffer, REPEAT / LINEAR / normalized
+ * (MinimalOptiX.cpp:445-474).  texels: w*h RGBA float, row 0 = bottom.
+ * Ids start at 1; 0 == RT_TEXTURE_ID_NULL. */
+int mox_add_texture_rgba32f(mox_ctx*, const float* texels, int w, int h, int* out_id);
+
+/* createGeometry(sphere|quad) + createMaterial + createGeometryInstance
+ * (MinimalOptiX.cpp:174-240, 495-518).  *out_prim_id (may be NULL) receives the
+ * global primitive id. */
+int mox_add_sphere(mox_ctx*, const SphereParams*, int material_kind, const void* material_params,
+                   uint32_t* out_prim_id);
+int mox_add_quad(mox_ctx*, const QuadParams*, int material_kind, const void* material_params,
+                 uint32_t* out_prim_id);
+
+/* One OBJ shape: vertexBuffer / normalBuffer / texcoordBuffer and the three int3
+ * index buffers (MinimalOptiX.cpp:392-441).  n_normals / n_texcoords may be 0
+ * (then nIdx / tIdx may be NULL).  *out_first_prim_id: id of face 0. */
+int mox_add_mesh(mox_ctx*, const float* vertices, size_t n_vertices, const float* normals,
+                 size_t n_normals, const float* texcoords, size_t n_texcoords,
+                 const int32_t* vIdx, const int32_t* nIdx, const int32_t* tIdx, size_t n_faces,
+                 int material_kind, const void* material_params, uint32_t* out_first_prim_id);
+
+/* context["lights"] buffer used by the Disney NEE loop (MinimalOptiX.cpp:523-531,
+ * Material.cu:116,172). */
+int mox_set_lights(mox_ctx*, const LightParams*, size_t n);
+
+/* Drop all geometry, materials, lights and the acceleration structure. */
+int mox_clear_scene(mox_ctx*);
+
+/* The moment OptiX builds Trbvh (context->validate() + first launch,
+ * MinimalOptiX.cpp:378,494,534,542): uploads the scene and builds the BVH on
+ * the GPU.  *out_build_ms (may be NULL): device time of the build kernels. */
+int mox_build_accel(mox_ctx*, uint32_t flags, float* out_build_ms);
+
+/* ---- render -------------------------------------------------------------- */
+
+/* context["randSeed"]->setInt(seed); context->launch(0, W, H)
+ * (MinimalOptiX.cpp:545-546): adds one sample per (owned) pixel to the
+ * accumulation buffer. */
+int mox_launch(mox_ctx*, int32_t randSeed);
+
+/* The spp loop of renderScene (MinimalOptiX.cpp:544-554) with a FIXED seed
+ * schedule instead of std::random_device: launch k (counted from the last
+ * clear) uses randSeed = (int32) tea<16>(k, seed).  Samples may be batched into
+ * one wavefront; the result is bit-identical to spp calls of mox_launch. */
+int mox_render(mox_ctx*, uint32_t spp, uint32_t seed);
+
+/* accuBuffer map()/unmap() (MinimalOptiX.cpp:44,60): W*H*3 floats, row 0 =
+ * bottom of the image, un-normalised sums.  Pixels of other ranks are 0. */
+int mox_read_accum(mox_ctx*, float* dst_rgb);
+int mox_clear_accum(mox_ctx*);
+
+/* Multi-GPU gather plumbing (device pointers on this context's GPU).
+ * mox_owned_pixels: number of pixels rank `rank` of the current partition owns.
+ * mox_pack_owned: copy this rank's owned pixels (tile order) to dev_dst
+ *   (3 floats per pixel).
+ * mox_unpack_owned: scatter a packed buffer produced by `rank` into this
+ *   context's full accumulation buffer (overwrites those pixels). */
+int mox_owned_pixels(mox_ctx*, uint32_t rank, uint64_t* out_n);
+int mox_pack_owned(mox_ctx*, void* dev_dst);
+int mox_unpack_owned(mox_ctx*, uint32_t rank, const void* dev_src);
+
+int mox_get_stats(mox_ctx*, mox_stats*);
+
+/* ---- raw ray queries (BASELINE config 5, primitive-id parity) -------------- */
+
+/* Closest hit for n rays.  rays: n x 8 floats (ox oy oz tmin dx dy dz tmax).
+ * hits: n x 4 x 32 bit: (float t, int32 prim id or -1, float beta, float gamma).
+ * Host-pointer and device-pointer variants; the device variant is what the
+ * resident benchmark times (*out_ms, may be NULL, is the kernel time). */
+int mox_trace_closest(mox_ctx*, const float* rays, size_t n, void* hits);
+int mox_trace_closest_device(mox_ctx*, const void* dev_rays, size_t n, void* dev_hits,
+                             float* out_ms);
+/* Shadow-ray transmittance (row a-11): out: n x 3 floats. */
+int mox_trace_shadow(mox_ctx*, const float* rays, size_t n, float* out_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOX_H */

@@ -1,0 +1,21 @@
+#include "api_table.h"
+#include <dlfcn.h>
+
+bool loadMoxApi(const char* libPath, const char* prefix, MoxApi& api, std::string& err) {
+  void* lib = dlopen(libPath, RTLD_NOW | RTLD_LOCAL);
+  if (!lib) { err = std::string("dlopen failed: ") + dlerror(); return false; }
+  api.lib = lib;
+  bool ok = true;
+  auto bind = [&](const char* name, void** slot) {
+    std::string sym = std::string(prefix) + name;
+    *slot = dlsym(lib, sym.c_str());
+    if (!*slot) { err += "missing symbol " + sym + "; "; ok = false; }
+  };
+#define BIND(n) bind(#n, (void**)&api.n)
+  BIND(create); BIND(destroy); BIND(last_error); BIND(set_globals); BIND(set_camera); BIND(set_rng_mode);
+  BIND(set_partition); BIND(add_texture_rgba32f); BIND(add_sphere); BIND(add_quad); BIND(add_mesh);
+  BIND(set_lights); BIND(clear_scene); BIND(build_accel); BIND(launch); BIND(render); BIND(read_accum);
+  BIND(clear_accum); BIND(get_stats);
+#undef BIND
+  return ok;
+}
