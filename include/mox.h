@@ -78,6 +78,10 @@ typedef struct mox_stats {
   uint32_t node_bytes;        /* bytes per node record                            */
   uint32_t prim_bytes;        /* bytes per packed triangle record                 */
   uint32_t n_lights;
+  /* per-stage device time (CUDA events on the launching stream) and launch counts since the last clear */
+  double ms_generate, ms_extend, ms_shade, ms_shadow, ms_accumulate;
+  uint64_t extend_launches;   /* closest-hit traversal kernel launches                   */
+  uint64_t kernel_launches;   /* all kernels this library launched for launch/render     */
 } mox_stats;
 
 /* ---- context ------------------------------------------------------------- */

@@ -47,7 +47,8 @@ SIGNATURES = {
     "trace_shadow": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
 }
 # Only the GPU library has the device-pointer query.
-GPU_ONLY = {"trace_closest_device": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.POINTER(_f32)])}
+GPU_ONLY = {"trace_closest_device": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.POINTER(_f32)]),
+            "debug_radix_sort": (C.c_int, [_vp, _vp, _vp, C.c_size_t])}
 
 
 class MoxError(RuntimeError):
@@ -218,6 +219,12 @@ class Context:
         ms = _f32()
         self._ck(self.b.trace_closest_device(self.h, _vp(rays_ptr), n, _vp(hits_ptr), C.byref(ms)), "trace_closest_device")
         return ms.value
+
+    def debug_radix_sort(self, keys, vals):
+        k = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+        v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._ck(self.b.debug_radix_sort(self.h, _ptr(k), _ptr(v), len(k)), "debug_radix_sort")
+        return k, v
 
     def trace_shadow(self, rays):
         r = _f32c(rays).reshape(-1, 8)

@@ -1,0 +1,756 @@
+// capi.cu — implementation of the C ABI in include/mox.h: context, scene staging and upload,
+// acceleration build, the spp loop, accumulation read-back, multi-GPU pack/unpack, raw ray
+// queries.  Host-side counterpart of what MinimalOptiX::setupContext / setupScene /
+// renderScene do through optixpp (MinimalOptiX.cpp:130-152, 154-538, 540-560).
+//
+// There is no CPU path in this library: every compute entry point needs a usable sm_100 GPU.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "build.h"
+#include "mox.h"
+#include "rng.cuh"
+#include "wavefront.h"
+
+namespace {
+std::string g_createError;
+
+enum Stage { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_ACCUMULATE, ST_COUNT };
+
+// Event pairs around the kernels of each stage; summed after the batch's final synchronize.
+struct StageTimer {
+  std::vector<cudaEvent_t> pool;
+  struct Span { int stage; size_t e0, e1; };
+  std::vector<Span> spans;
+  size_t used = 0;
+  size_t grab(cudaStream_t s) {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    cudaEventRecord(pool[used], s);
+    return used++;
+  }
+  void begin(int stage, cudaStream_t s) { spans.push_back({stage, grab(s), 0}); }
+  void end(cudaStream_t s) { spans.back().e1 = grab(s); }
+  void collect(double* ms) {
+    for (auto& sp : spans) { float t = 0; if (cudaEventElapsedTime(&t, pool[sp.e0], pool[sp.e1]) == cudaSuccess) ms[sp.stage] += t; }
+    spans.clear(); used = 0;
+  }
+  void release() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+}  // namespace
+
+struct mox_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  RenderParams rp{};
+  bool haveGlobals = false, haveCamera = false;
+  uint32_t rank = 0, world = 1, tile = 32;
+
+  // host staging of the scene (copied at add_* time)
+  std::vector<PrimDesc> prims;
+  std::vector<TriIdx> tris;
+  std::vector<float> verts, normals, uvs;
+  std::vector<Analytic> analytic;
+  std::vector<GpuMaterial> mats;
+  std::vector<LightParams> lights;
+  uint32_t nSpheres = 0, nQuads = 0;
+
+  // device scene
+  DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights;
+  BvhNode2* dNodes = nullptr;
+  float4* dPacked = nullptr;
+  int nNodes = 0, nValid = 0;
+  bool built = false, lightsDirty = true;
+  uint32_t accelFlags = 0;
+
+  // image
+  float* dAccu = nullptr;
+  uint32_t accuW = 0, accuH = 0;
+  uint32_t* dOwned = nullptr;
+  uint32_t nOwned = 0;
+  bool ownedDirty = true;
+  std::vector<DevBuf> otherOwned;  // cached owned lists of other ranks (unpack)
+
+  PathBuffers pb;
+  float* pinned = nullptr;
+  size_t pinnedBytes = 0;
+
+  // stats
+  uint64_t raysPrimary = 0, raysBounce = 0, raysShadow = 0, nonfinite = 0, launches = 0, nodeVisits = 0, primTests = 0;
+  double msRender = 0, msBuild = 0;
+  double msStage[ST_COUNT] = {0, 0, 0, 0, 0};
+  uint64_t extendLaunches = 0, kernelLaunches = 0;
+  StageTimer timer;
+  size_t maxBatchPaths = 4u << 20;
+};
+
+namespace {
+
+int fail(mox_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_createError = msg;
+  return code;
+}
+
+#define CUCK(c, x)                                                                                    \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail((c), e_ == cudaErrorMemoryAllocation ? MOX_ERR_OOM : MOX_ERR_CUDA, \
+                                       std::string(#x) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+int bind(mox_ctx* c) {
+  CUCK(c, cudaSetDevice(c->device));
+  return MOX_OK;
+}
+
+int ensure(mox_ctx* c, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return MOX_OK;
+  b.release();
+  CUCK(c, cudaMalloc(&b.p, std::max<size_t>(bytes, 16)));
+  b.bytes = std::max<size_t>(bytes, 16);
+  return MOX_OK;
+}
+
+template <class T>
+int upload(mox_ctx* c, DevBuf& b, const std::vector<T>& v) {
+  int rc = ensure(c, b, v.size() * sizeof(T));
+  if (rc) return rc;
+  if (!v.empty()) CUCK(c, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return MOX_OK;
+}
+
+int addMaterial(mox_ctx* c, int kind, const void* params) {
+  GpuMaterial m;
+  memset(&m, 0, sizeof m);
+  m.kind = kind;
+  switch (kind) {
+    case MOX_MAT_LAMBERTIAN: memcpy(&m.lam, params, sizeof(LambertianParams)); break;
+    case MOX_MAT_METAL: memcpy(&m.met, params, sizeof(MetalParams)); break;
+    case MOX_MAT_GLASS: memcpy(&m.gls, params, sizeof(GlassParams)); break;
+    case MOX_MAT_DISNEY: memcpy(&m.dis, params, sizeof(DisneyParams)); break;
+    case MOX_MAT_LIGHT: memcpy(&m.lgt, params, sizeof(LightParams)); break;
+    default: return -1;
+  }
+  c->mats.push_back(m);
+  return (int)c->mats.size() - 1;
+}
+
+void ownedList(uint32_t W, uint32_t H, uint32_t tile, uint32_t world, uint32_t rank, std::vector<uint32_t>& out) {
+  out.clear();
+  uint32_t tx = (W + tile - 1) / tile, ty = (H + tile - 1) / tile;
+  for (uint32_t j = 0; j < ty; ++j)
+    for (uint32_t i = 0; i < tx; ++i) {
+      if ((i + j) % world != rank) continue;
+      for (uint32_t y = j * tile; y < std::min(H, (j + 1) * tile); ++y)
+        for (uint32_t x = i * tile; x < std::min(W, (i + 1) * tile); ++x) out.push_back(y * W + x);
+    }
+}
+
+int refreshOwned(mox_ctx* c) {
+  if (!c->ownedDirty) return MOX_OK;
+  std::vector<uint32_t> l;
+  ownedList(c->rp.W, c->rp.H, c->tile, c->world, c->rank, l);
+  if (c->dOwned) cudaFree(c->dOwned);
+  c->dOwned = nullptr;
+  CUCK(c, cudaMalloc(&c->dOwned, std::max<size_t>(l.size(), 1) * 4));
+  if (!l.empty()) CUCK(c, cudaMemcpy(c->dOwned, l.data(), l.size() * 4, cudaMemcpyHostToDevice));
+  c->nOwned = (uint32_t)l.size();
+  for (auto& b : c->otherOwned) b.release();
+  c->otherOwned.clear();
+  c->ownedDirty = false;
+  return MOX_OK;
+}
+
+void freePaths(PathBuffers& pb) {
+  cudaFree(pb.rayO); cudaFree(pb.rayD); cudaFree(pb.hit); cudaFree(pb.thr); cudaFree(pb.rad); cudaFree(pb.state);
+  cudaFree(pb.qCur); cudaFree(pb.qNext);
+  for (auto& q : pb.qMat) cudaFree(q);
+  cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.counters); cudaFree(pb.seeds);
+  pb = PathBuffers();
+}
+
+int ensurePaths(mox_ctx* c, size_t paths, size_t nLights, size_t nSeeds) {
+  PathBuffers& pb = c->pb;
+  size_t slots = paths * nLights;
+  if (pb.capacity < paths || pb.shadowSlots < slots || !pb.counters) {
+    cudaStreamSynchronize(c->stream);
+    size_t seedCap = pb.seedCap;
+    int32_t* seeds = pb.seeds;
+    pb.seeds = nullptr;
+    freePaths(pb);
+    pb.seeds = seeds; pb.seedCap = seedCap;
+    CUCK(c, cudaMalloc(&pb.rayO, paths * 16)); CUCK(c, cudaMalloc(&pb.rayD, paths * 16));
+    CUCK(c, cudaMalloc(&pb.hit, paths * 16)); CUCK(c, cudaMalloc(&pb.thr, paths * 16));
+    CUCK(c, cudaMalloc(&pb.rad, paths * 16)); CUCK(c, cudaMalloc(&pb.state, paths * 4));
+    CUCK(c, cudaMalloc(&pb.qCur, paths * 4)); CUCK(c, cudaMalloc(&pb.qNext, paths * 4));
+    for (auto& q : pb.qMat) CUCK(c, cudaMalloc(&q, paths * 4));
+    if (slots) {
+      CUCK(c, cudaMalloc(&pb.shO, slots * 16)); CUCK(c, cudaMalloc(&pb.shD, slots * 16)); CUCK(c, cudaMalloc(&pb.shC, slots * 16));
+    }
+    CUCK(c, cudaMalloc(&pb.counters, C_WORDS * 4));
+    CUCK(c, cudaMemset(pb.counters, 0, C_WORDS * 4));
+    pb.capacity = paths; pb.shadowSlots = slots;
+  }
+  if (pb.seedCap < nSeeds) {
+    cudaFree(pb.seeds);
+    pb.seeds = nullptr;
+    CUCK(c, cudaMalloc(&pb.seeds, nSeeds * 4));
+    pb.seedCap = nSeeds;
+  }
+  return MOX_OK;
+}
+
+SceneView sceneView(const mox_ctx* c) {
+  SceneView s;
+  s.nodes = c->dNodes;
+  s.packed = c->dPacked;
+  s.analytic = (const Analytic*)c->dAnalytic.p;
+  s.prims = (const PrimDesc*)c->dPrims.p;
+  s.mats = (const GpuMaterial*)c->dMats.p;
+  s.verts = (const float*)c->dVerts.p;
+  s.normals = (const float*)c->dNormals.p;
+  s.uvs = (const float*)c->dUvs.p;
+  s.tris = (const TriIdx*)c->dTris.p;
+  s.lights = (const LightParams*)c->dLights.p;
+  s.nLights = (int)c->lights.size();
+  s.nPrims = (int)c->prims.size();
+  return s;
+}
+
+int syncLights(mox_ctx* c) {
+  if (!c->lightsDirty) return MOX_OK;
+  int rc = upload(c, c->dLights, c->lights);
+  if (rc) return rc;
+  c->lightsDirty = false;
+  return MOX_OK;
+}
+
+// One wavefront batch: `seeds.size()` samples of every owned pixel.
+int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
+  const uint32_t S = (uint32_t)seeds.size();
+  const size_t P = (size_t)S * c->nOwned;
+  if (P == 0) return MOX_OK;
+  if (P > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "batch too large");
+  int rc = ensurePaths(c, P, c->lights.size(), S);
+  if (rc) return rc;
+  PathBuffers& pb = c->pb;
+  CUCK(c, cudaMemcpyAsync(pb.seeds, seeds.data(), S * 4, cudaMemcpyHostToDevice, c->stream));
+  LaunchCtx lc;
+  lc.scene = sceneView(c);
+  lc.rp = c->rp;
+  lc.pb = pb;
+  lc.ownedPix = c->dOwned;
+  lc.nOwned = c->nOwned;
+  lc.accu = c->dAccu;
+  lc.countTraversal = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
+  lc.stream = c->stream;
+
+  CUCK(c, cudaMemsetAsync(pb.counters, 0, C_WORDS * 4, c->stream));
+  StageTimer& tm = c->timer;
+  tm.begin(ST_GENERATE, c->stream);
+  launchGenerate(lc, S);
+  tm.end(c->stream);
+  c->kernelLaunches++;
+  uint32_t count = (uint32_t)P;
+  uint32_t host[C_WORDS];
+  for (uint32_t depth = 1; count > 0; ++depth) {
+    if (depth == 1) c->raysPrimary += count; else c->raysBounce += count;
+    tm.begin(ST_EXTEND, c->stream);
+    launchExtend(lc, lc.pb.qCur, count, depth);
+    tm.end(c->stream);
+    c->extendLaunches++; c->kernelLaunches++;
+    CUCK(c, cudaMemcpyAsync(host, pb.counters, 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUCK(c, cudaStreamSynchronize(c->stream));
+    uint32_t matCount[Q_COUNT];
+    uint32_t any = 0;
+    for (int k = 0; k < Q_COUNT; ++k) { matCount[k] = host[C_MAT0 + k]; any += matCount[k]; }
+    if (!any) break;
+    tm.begin(ST_SHADE, c->stream);
+    for (int k = 0; k < Q_COUNT; ++k) { launchShade(lc, k, matCount[k], depth); if (matCount[k]) c->kernelLaunches++; }
+    tm.end(c->stream);
+    if (matCount[Q_DISNEY] && lc.scene.nLights) {
+      tm.begin(ST_SHADOW, c->stream);
+      launchShadowAndApply(lc, matCount[Q_DISNEY]);
+      tm.end(c->stream);
+      c->kernelLaunches += 2;
+    }
+    CUCK(c, cudaMemcpyAsync(host, pb.counters, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUCK(c, cudaMemsetAsync(pb.counters, 0, 8 * 4, c->stream));  // next count + material counts
+    CUCK(c, cudaStreamSynchronize(c->stream));
+    count = host[C_NEXT];
+    std::swap(lc.pb.qCur, lc.pb.qNext);
+  }
+  tm.begin(ST_ACCUMULATE, c->stream);
+  launchAccumulate(lc, S);
+  tm.end(c->stream);
+  c->kernelLaunches++;
+  CUCK(c, cudaMemcpyAsync(host, pb.counters, C_WORDS * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  CUCK(c, cudaGetLastError());
+  tm.collect(c->msStage);
+  c->nonfinite += host[C_NONFINITE];
+  c->raysShadow += host[C_SHADOW];
+  c->nodeVisits += ((uint64_t)host[C_NODEVIS_HI] << 32) | host[C_NODEVIS_LO];
+  c->primTests += ((uint64_t)host[C_PRIMTEST_HI] << 32) | host[C_PRIMTEST_LO];
+  c->launches += S;
+  return MOX_OK;
+}
+
+int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
+  if (!c->built) return fail(c, MOX_ERR_STATE, "launch before mox_build_accel");
+  if (!c->haveGlobals) return fail(c, MOX_ERR_STATE, "launch before mox_set_globals");
+  if (!c->haveCamera) return fail(c, MOX_ERR_STATE, "launch before mox_set_camera");
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = refreshOwned(c))) return rc;
+  if ((rc = syncLights(c))) return rc;
+  if (c->nOwned == 0) { c->launches += seeds.size(); return MOX_OK; }
+  size_t perBatch = std::max<size_t>(1, c->maxBatchPaths / c->nOwned);
+  CUCK(c, cudaEventRecord(c->ev0, c->stream));
+  for (size_t i = 0; i < seeds.size(); i += perBatch) {
+    std::vector<int32_t> chunk(seeds.begin() + i, seeds.begin() + std::min(seeds.size(), i + perBatch));
+    if ((rc = renderBatch(c, chunk))) return rc;
+  }
+  CUCK(c, cudaEventRecord(c->ev1, c->stream));
+  CUCK(c, cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUCK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->msRender += ms;
+  return MOX_OK;
+}
+
+int ensurePinned(mox_ctx* c, size_t bytes) {
+  if (c->pinnedBytes >= bytes) return MOX_OK;
+  if (c->pinned) cudaFreeHost(c->pinned);
+  c->pinned = nullptr; c->pinnedBytes = 0;
+  CUCK(c, cudaMallocHost(&c->pinned, bytes));
+  c->pinnedBytes = bytes;
+  return MOX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mox_abi_version(void) { return MOX_ABI_VERSION; }
+
+const char* mox_last_error(const mox_ctx* c) { return c ? c->err.c_str() : g_createError.c_str(); }
+
+int mox_create(mox_ctx** out, int device_id) {
+  if (!out) return fail(nullptr, MOX_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, MOX_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                           " (this library has no CPU fallback)");
+  if (device_id < 0 || device_id >= n) return fail(nullptr, MOX_ERR_INVALID, "device_id out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return fail(nullptr, MOX_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, MOX_ERR_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                           "; libmox.so contains sm_100a code only");
+  mox_ctx* c = new mox_ctx();
+  c->device = device_id;
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+    std::string msg = cudaGetErrorString(e);
+    delete c;
+    return fail(nullptr, MOX_ERR_CUDA, msg);
+  }
+  if (const char* env = getenv("MOX_MAX_BATCH_PATHS")) { long long v = atoll(env); if (v > 0) c->maxBatchPaths = (size_t)v; }
+  memset(&c->rp, 0, sizeof c->rp);
+  c->rp.maxDepth = 256; c->rp.eps = 0.001f; c->rp.minIntensity = 0.001f;
+  c->rp.bad = make_float3(1.f, 1.f, 1.f);
+  *out = c;
+  return MOX_OK;
+}
+
+void mox_destroy(mox_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights}) b->release();
+  for (auto& b : c->otherOwned) b.release();
+  cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dAccu); cudaFree(c->dOwned);
+  freePaths(c->pb);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  c->timer.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mox_set_globals(mox_ctx* c, uint32_t width, uint32_t height, uint32_t rayMaxDepth, float rayEpsilonT, float rayMinIntensity,
+                    const float absorbColor[3], const float badColor[3], const float bgColor[3]) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!width || !height || !absorbColor || !badColor || !bgColor) return fail(c, MOX_ERR_INVALID, "bad globals");
+  if ((uint64_t)width * height > 0x7fffffffull / 3) return fail(c, MOX_ERR_INVALID, "image too large");
+  int rc = bind(c);
+  if (rc) return rc;
+  if (width != c->accuW || height != c->accuH || !c->dAccu) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->dAccu);
+    c->dAccu = nullptr;
+    CUCK(c, cudaMalloc(&c->dAccu, (size_t)width * height * 12));
+    CUCK(c, cudaMemset(c->dAccu, 0, (size_t)width * height * 12));
+    c->accuW = width; c->accuH = height;
+    c->launches = 0;
+    c->ownedDirty = true;
+  }
+  c->rp.W = width; c->rp.H = height; c->rp.maxDepth = rayMaxDepth; c->rp.eps = rayEpsilonT; c->rp.minIntensity = rayMinIntensity;
+  c->rp.absorb = make_float3(absorbColor[0], absorbColor[1], absorbColor[2]);
+  c->rp.bad = make_float3(badColor[0], badColor[1], badColor[2]);
+  c->rp.bg = make_float3(bgColor[0], bgColor[1], bgColor[2]);
+  c->haveGlobals = true;
+  return MOX_OK;
+}
+
+int mox_set_camera(mox_ctx* c, const CamParams* cam) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!cam) return fail(c, MOX_ERR_INVALID, "null camera");
+  c->rp.cam = *cam;
+  c->haveCamera = true;
+  return MOX_OK;
+}
+
+int mox_set_rng_mode(mox_ctx* c, int mode) {
+  if (!c) return MOX_ERR_INVALID;
+  if (mode != MOX_RNG_REF && mode != MOX_RNG_PHILOX) return fail(c, MOX_ERR_INVALID, "bad rng mode");
+  c->rp.rngMode = mode;
+  return MOX_OK;
+}
+
+int mox_set_partition(mox_ctx* c, uint32_t rank, uint32_t world, uint32_t tile) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!world || rank >= world || !tile) return fail(c, MOX_ERR_INVALID, "bad partition");
+  c->rank = rank; c->world = world; c->tile = tile;
+  c->ownedDirty = true;
+  return MOX_OK;
+}
+
+int mox_add_texture_rgba32f(mox_ctx* c, const float*, int, int, int*) {
+  if (!c) return MOX_ERR_INVALID;
+  return fail(c, MOX_ERR_INVALID, "textures are not built yet (SURVEY.md §8 f-1)");
+}
+
+int mox_add_sphere(mox_ctx* c, const SphereParams* s, int kind, const void* params, uint32_t* out_id) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!s || !params) return fail(c, MOX_ERR_INVALID, "null argument");
+  int m = addMaterial(c, kind, params);
+  if (m < 0) return fail(c, MOX_ERR_INVALID, "bad material kind");
+  Analytic a;
+  memset(&a, 0, sizeof a);
+  a.a = make_float4(s->center.x, s->center.y, s->center.z, s->radius);
+  c->analytic.push_back(a);
+  c->prims.push_back({PT_SPHERE | ((uint32_t)m << 2), (uint32_t)c->analytic.size() - 1});
+  c->nSpheres++;
+  if (out_id) *out_id = (uint32_t)c->prims.size() - 1;
+  c->built = false;
+  return MOX_OK;
+}
+
+int mox_add_quad(mox_ctx* c, const QuadParams* q, int kind, const void* params, uint32_t* out_id) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!q || !params) return fail(c, MOX_ERR_INVALID, "null argument");
+  int m = addMaterial(c, kind, params);
+  if (m < 0) return fail(c, MOX_ERR_INVALID, "bad material kind");
+  Analytic a;
+  a.a = make_float4(q->plane.x, q->plane.y, q->plane.z, q->plane.w);
+  a.b = make_float4(q->v1.x, q->v1.y, q->v1.z, 0.f);
+  a.c = make_float4(q->v2.x, q->v2.y, q->v2.z, 0.f);
+  a.d = make_float4(q->anchor.x, q->anchor.y, q->anchor.z, 0.f);
+  c->analytic.push_back(a);
+  c->prims.push_back({PT_QUAD | ((uint32_t)m << 2), (uint32_t)c->analytic.size() - 1});
+  c->nQuads++;
+  if (out_id) *out_id = (uint32_t)c->prims.size() - 1;
+  c->built = false;
+  return MOX_OK;
+}
+
+int mox_add_mesh(mox_ctx* c, const float* v, size_t nv, const float* n, size_t nn, const float* uv, size_t nt, const int32_t* vIdx,
+                 const int32_t* nIdx, const int32_t* tIdx, size_t nFaces, int kind, const void* params, uint32_t* out_first) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!params || (nFaces && (!v || !vIdx))) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (c->prims.size() + nFaces >= (1u << 30)) return fail(c, MOX_ERR_INVALID, "too many primitives");
+  int m = addMaterial(c, kind, params);
+  if (m < 0) return fail(c, MOX_ERR_INVALID, "bad material kind");
+  bool hasN = nn > 0 && n && nIdx, hasT = nt > 0 && uv && tIdx;
+  for (size_t f = 0; f < nFaces * 3; ++f) {
+    if (vIdx[f] < 0 || (size_t)vIdx[f] >= nv) { c->mats.pop_back(); return fail(c, MOX_ERR_INVALID, "vertex index out of range"); }
+    if (hasN && (nIdx[f] < 0 || (size_t)nIdx[f] >= nn)) hasN = false;
+    if (hasT && (tIdx[f] < 0 || (size_t)tIdx[f] >= nt)) hasT = false;
+  }
+  int vb = (int)(c->verts.size() / 3), nb = (int)(c->normals.size() / 3), tb = (int)(c->uvs.size() / 2);
+  c->verts.insert(c->verts.end(), v, v + nv * 3);
+  if (hasN) c->normals.insert(c->normals.end(), n, n + nn * 3);
+  if (hasT) c->uvs.insert(c->uvs.end(), uv, uv + nt * 2);
+  if (out_first) *out_first = (uint32_t)c->prims.size();
+  c->tris.reserve(c->tris.size() + nFaces);
+  c->prims.reserve(c->prims.size() + nFaces);
+  for (size_t f = 0; f < nFaces; ++f) {
+    TriIdx t;
+    for (int k = 0; k < 3; ++k) {
+      t.v[k] = vb + vIdx[3 * f + k];
+      t.n[k] = hasN ? nb + nIdx[3 * f + k] : -1;
+      t.t[k] = hasT ? tb + tIdx[3 * f + k] : -1;
+    }
+    c->tris.push_back(t);
+    c->prims.push_back({PT_TRI | ((uint32_t)m << 2), (uint32_t)c->tris.size() - 1});
+  }
+  c->built = false;
+  return MOX_OK;
+}
+
+int mox_set_lights(mox_ctx* c, const LightParams* l, size_t n) {
+  if (!c) return MOX_ERR_INVALID;
+  if (n && !l) return fail(c, MOX_ERR_INVALID, "null lights");
+  c->lights.assign(l, l + n);
+  c->lightsDirty = true;
+  return MOX_OK;
+}
+
+int mox_clear_scene(mox_ctx* c) {
+  if (!c) return MOX_ERR_INVALID;
+  c->prims.clear(); c->tris.clear(); c->verts.clear(); c->normals.clear(); c->uvs.clear(); c->analytic.clear();
+  c->mats.clear(); c->lights.clear();
+  c->nSpheres = c->nQuads = 0;
+  c->built = false; c->lightsDirty = true;
+  return MOX_OK;
+}
+
+int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
+  if (!c) return MOX_ERR_INVALID;
+  int rc = bind(c);
+  if (rc) return rc;
+  cudaStreamSynchronize(c->stream);
+  if ((rc = upload(c, c->dPrims, c->prims))) return rc;
+  if ((rc = upload(c, c->dTris, c->tris))) return rc;
+  if ((rc = upload(c, c->dVerts, c->verts))) return rc;
+  if ((rc = upload(c, c->dNormals, c->normals))) return rc;
+  if ((rc = upload(c, c->dUvs, c->uvs))) return rc;
+  if ((rc = upload(c, c->dAnalytic, c->analytic))) return rc;
+  if ((rc = upload(c, c->dMats, c->mats))) return rc;
+  if ((rc = syncLights(c))) return rc;
+  cudaFree(c->dNodes); cudaFree(c->dPacked);
+  c->dNodes = nullptr; c->dPacked = nullptr;
+  BuildInput in;
+  in.nPrims = (int)c->prims.size();
+  in.prims = (const PrimDesc*)c->dPrims.p;
+  in.tris = (const TriIdx*)c->dTris.p;
+  in.verts = (const float*)c->dVerts.p;
+  in.analytic = (const Analytic*)c->dAnalytic.p;
+  in.evStart = c->ev0; in.evStop = c->ev1;
+  BuildOutput out;
+  std::string err;
+  if (!buildBvh(in, out, c->stream, err)) return fail(c, MOX_ERR_CUDA, "build_accel: " + err);
+  CUCK(c, cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUCK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->dNodes = out.nodes; c->dPacked = out.packed; c->nNodes = out.nNodes; c->nValid = out.nValid;
+  c->msBuild = ms;
+  c->accelFlags = flags;
+  c->built = true;
+  if (out_ms) *out_ms = ms;
+  return MOX_OK;
+}
+
+int mox_launch(mox_ctx* c, int32_t randSeed) {
+  if (!c) return MOX_ERR_INVALID;
+  return renderSeeds(c, std::vector<int32_t>{randSeed});
+}
+
+int mox_render(mox_ctx* c, uint32_t spp, uint32_t seed) {
+  if (!c) return MOX_ERR_INVALID;
+  std::vector<int32_t> seeds(spp);
+  for (uint32_t i = 0; i < spp; ++i) seeds[i] = (int32_t)tea16((uint32_t)(c->launches + i), seed);
+  return renderSeeds(c, seeds);
+}
+
+int mox_read_accum(mox_ctx* c, float* dst) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!dst || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
+  int rc = bind(c);
+  if (rc) return rc;
+  size_t bytes = (size_t)c->accuW * c->accuH * 12;
+  if ((rc = ensurePinned(c, bytes))) return rc;
+  CUCK(c, cudaMemcpyAsync(c->pinned, c->dAccu, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  memcpy(dst, c->pinned, bytes);
+  return MOX_OK;
+}
+
+int mox_clear_accum(mox_ctx* c) {
+  if (!c) return MOX_ERR_INVALID;
+  int rc = bind(c);
+  if (rc) return rc;
+  if (c->dAccu) CUCK(c, cudaMemsetAsync(c->dAccu, 0, (size_t)c->accuW * c->accuH * 12, c->stream));
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  c->launches = 0; c->raysPrimary = c->raysBounce = c->raysShadow = c->nonfinite = c->nodeVisits = c->primTests = 0;
+  c->msRender = 0;
+  for (double& m : c->msStage) m = 0;
+  c->extendLaunches = c->kernelLaunches = 0;
+  return MOX_OK;
+}
+
+int mox_owned_pixels(mox_ctx* c, uint32_t rank, uint64_t* out_n) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!out_n || rank >= c->world || !c->haveGlobals) return fail(c, MOX_ERR_INVALID, "bad owned_pixels query");
+  std::vector<uint32_t> l;
+  ownedList(c->rp.W, c->rp.H, c->tile, c->world, rank, l);
+  *out_n = l.size();
+  return MOX_OK;
+}
+
+int mox_pack_owned(mox_ctx* c, void* dev_dst) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!dev_dst || !c->dAccu) return fail(c, MOX_ERR_INVALID, "bad pack_owned");
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = refreshOwned(c))) return rc;
+  launchPackOwned(c->dAccu, c->dOwned, c->nOwned, (float*)dev_dst, c->stream);
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  return MOX_OK;
+}
+
+int mox_unpack_owned(mox_ctx* c, uint32_t rank, const void* dev_src) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!dev_src || !c->dAccu || rank >= c->world) return fail(c, MOX_ERR_INVALID, "bad unpack_owned");
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = refreshOwned(c))) return rc;
+  if (c->otherOwned.size() != c->world) c->otherOwned.resize(c->world);
+  std::vector<uint32_t> l;
+  ownedList(c->rp.W, c->rp.H, c->tile, c->world, rank, l);
+  DevBuf& b = c->otherOwned[rank];
+  if (!b.p) {
+    if ((rc = ensure(c, b, l.size() * 4))) return rc;
+    if (!l.empty()) CUCK(c, cudaMemcpy(b.p, l.data(), l.size() * 4, cudaMemcpyHostToDevice));
+  }
+  launchUnpackOwned(c->dAccu, (const uint32_t*)b.p, (uint32_t)l.size(), (const float*)dev_src, c->stream);
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  return MOX_OK;
+}
+
+int mox_get_stats(mox_ctx* c, mox_stats* s) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!s) return fail(c, MOX_ERR_INVALID, "null stats");
+  memset(s, 0, sizeof *s);
+  s->rays_primary = c->raysPrimary; s->rays_bounce = c->raysBounce; s->rays_shadow = c->raysShadow;
+  s->nonfinite_samples = c->nonfinite; s->launches = c->launches; s->node_visits = c->nodeVisits; s->prim_tests = c->primTests;
+  s->ms_render = c->msRender; s->ms_build = c->msBuild;
+  s->n_prims = (uint32_t)c->prims.size(); s->n_triangles = (uint32_t)c->tris.size();
+  s->n_spheres = c->nSpheres; s->n_quads = c->nQuads;
+  s->n_nodes = (uint32_t)c->nNodes; s->node_bytes = sizeof(BvhNode2); s->prim_bytes = 16 * MOX_PACKED_F4;
+  s->n_lights = (uint32_t)c->lights.size();
+  s->ms_generate = c->msStage[ST_GENERATE]; s->ms_extend = c->msStage[ST_EXTEND]; s->ms_shade = c->msStage[ST_SHADE];
+  s->ms_shadow = c->msStage[ST_SHADOW]; s->ms_accumulate = c->msStage[ST_ACCUMULATE];
+  s->extend_launches = c->extendLaunches; s->kernel_launches = c->kernelLaunches;
+  return MOX_OK;
+}
+
+int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* dev_hits, float* out_ms) {
+  if (!c) return MOX_ERR_INVALID;
+  if (n && (!dev_rays || !dev_hits)) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
+  int rc = bind(c);
+  if (rc) return rc;
+  bool count = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
+  uint32_t* counters = nullptr;
+  if (count) {
+    if ((rc = ensurePaths(c, std::max<size_t>(c->pb.capacity, 1), c->lights.size(), 1))) return rc;
+    counters = c->pb.counters;
+    CUCK(c, cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream));
+  }
+  CUCK(c, cudaEventRecord(c->ev0, c->stream));
+  launchTraceClosest(sceneView(c), (const float4*)dev_rays, n, (float4*)dev_hits, count, counters, c->stream);
+  CUCK(c, cudaEventRecord(c->ev1, c->stream));
+  CUCK(c, cudaEventSynchronize(c->ev1));
+  CUCK(c, cudaGetLastError());
+  float ms = 0;
+  CUCK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (out_ms) *out_ms = ms;
+  if (count) {
+    uint32_t host[C_WORDS];
+    CUCK(c, cudaMemcpy(host, counters, sizeof host, cudaMemcpyDeviceToHost));
+    c->nodeVisits += ((uint64_t)host[C_NODEVIS_HI] << 32) | host[C_NODEVIS_LO];
+    c->primTests += ((uint64_t)host[C_PRIMTEST_HI] << 32) | host[C_PRIMTEST_LO];
+  }
+  return MOX_OK;
+}
+
+int mox_trace_closest(mox_ctx* c, const float* rays, size_t n, void* hits) {
+  if (!c) return MOX_ERR_INVALID;
+  if (n && (!rays || !hits)) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
+  if (!n) return MOX_OK;
+  int rc = bind(c);
+  if (rc) return rc;
+  void *dRays = nullptr, *dHits = nullptr;
+  CUCK(c, cudaMalloc(&dRays, n * 32));
+  CUCK(c, cudaMalloc(&dHits, n * 16));
+  CUCK(c, cudaMemcpy(dRays, rays, n * 32, cudaMemcpyHostToDevice));
+  rc = mox_trace_closest_device(c, dRays, n, dHits, nullptr);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(hits, dHits, n * 16, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(c, MOX_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(dRays); cudaFree(dHits);
+  return rc;
+}
+
+int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
+  if (!c) return MOX_ERR_INVALID;
+  if (n && (!rays || !out_rgb)) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
+  if (!n) return MOX_OK;
+  int rc = bind(c);
+  if (rc) return rc;
+  void *dRays = nullptr, *dOut = nullptr;
+  CUCK(c, cudaMalloc(&dRays, n * 32));
+  CUCK(c, cudaMalloc(&dOut, n * 12));
+  CUCK(c, cudaMemcpy(dRays, rays, n * 32, cudaMemcpyHostToDevice));
+  launchTraceShadow(sceneView(c), (const float4*)dRays, n, (float*)dOut, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out_rgb, dOut, n * 12, cudaMemcpyDeviceToHost);
+  cudaFree(dRays); cudaFree(dOut);
+  if (e != cudaSuccess) return fail(c, MOX_ERR_CUDA, cudaGetErrorString(e));
+  return MOX_OK;
+}
+
+}  // extern "C"
+
+// ---- debug / test hooks (not part of the drop-in surface; declared in include/mox_debug.h)
+extern "C" int mox_debug_radix_sort(mox_ctx* c, uint32_t* keys, uint32_t* vals, size_t n) {
+  if (!c) return MOX_ERR_INVALID;
+  if (n && (!keys || !vals)) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (!n) return MOX_OK;
+  int rc = bind(c);
+  if (rc) return rc;
+  uint32_t *dk = nullptr, *dv = nullptr;
+  CUCK(c, cudaMalloc(&dk, n * 4));
+  CUCK(c, cudaMalloc(&dv, n * 4));
+  CUCK(c, cudaMemcpy(dk, keys, n * 4, cudaMemcpyHostToDevice));
+  CUCK(c, cudaMemcpy(dv, vals, n * 4, cudaMemcpyHostToDevice));
+  std::string err;
+  bool ok = radixSortPairs(dk, dv, (int)n, c->stream, err);
+  if (ok) {
+    cudaMemcpy(keys, dk, n * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(vals, dv, n * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dk); cudaFree(dv);
+  return ok ? MOX_OK : fail(c, MOX_ERR_CUDA, err);
+}

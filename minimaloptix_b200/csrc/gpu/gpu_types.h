@@ -1,0 +1,69 @@
+// gpu_types.h — HBM data layout of a built scene (all arrays 16-byte aligned).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mox.h"
+
+enum PrimType : uint32_t { PT_TRI = 0, PT_SPHERE = 1, PT_QUAD = 2 };
+
+// 80-byte material record: kind + the reference's parameter struct verbatim.
+struct __align__(16) GpuMaterial {
+  int kind;  // mox_material_kind
+  int pad;
+  union {
+    LambertianParams lam;
+    MetalParams met;
+    GlassParams gls;
+    DisneyParams dis;
+    LightParams lgt;
+  };
+};
+static_assert(sizeof(GpuMaterial) == 80, "GpuMaterial");
+
+// Per primitive id: type (2 bits) | material index (30 bits); index into tris / analytic.
+struct PrimDesc { uint32_t typeMat; uint32_t geom; };
+
+// Global (mesh-base-added) indices of a triangle; n[0] < 0: no normals; t[0] < 0: no texcoords.
+struct TriIdx { int v[3]; int n[3]; int t[3]; };
+
+// Sphere: a = (center, radius).  Quad: a = plane, b = v1, c = v2, d = anchor (QuadParams).
+struct __align__(16) Analytic { float4 a, b, c, d; };
+
+// Binary BVH node in the Aila–Laine layout: both child boxes in the parent, 64 bytes.
+//   c0xy = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   c1xy likewise
+//   cz   = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   ref  = (child0, child1, -, -): >= 0 inner node index; < 0 leaf: ~((first << 3) | (count - 1))
+//          over the leaf-ordered packed primitive array; 0x80000000 = empty child.
+struct __align__(16) BvhNode2 { float4 c0xy, c1xy, cz; int4 ref; };
+static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
+#define MOX_EMPTY_CHILD ((int)0x80000000)
+#define MOX_LEAF_MAX 4
+
+// Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.
+//   triangle: (p0, idbits) (e0 = p1 - p0, -) (e1 = p0 - p2, -)
+//   analytic: (index into Analytic[] as int bits, -, -, idbits)
+// idbits = prim id | type << 30.
+#define MOX_PACKED_F4 3
+
+struct SceneView {
+  const BvhNode2* nodes;
+  const float4* packed;
+  const Analytic* analytic;
+  const PrimDesc* prims;
+  const GpuMaterial* mats;
+  const float* verts;    // xyz
+  const float* normals;  // xyz
+  const float* uvs;      // uv
+  const TriIdx* tris;
+  const LightParams* lights;
+  int nLights;
+  int nPrims;
+};
+
+struct RenderParams {
+  uint32_t W, H, maxDepth;
+  float eps, minIntensity;
+  float3 absorb, bad, bg;
+  CamParams cam;
+  int rngMode;
+};

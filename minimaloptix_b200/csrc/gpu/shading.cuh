@@ -1,0 +1,136 @@
+// shading.cuh — device-side material math: dielectric Fresnel, hit-point refinement, the
+// microfacet helpers and the Disney BRDF sample / pdf / eval.
+// Semantics: MinimalOptiX/utils_device.h:63-185 and disney.h:9-91 (quirks kept: sampling uses
+// alpha = roughness while eval uses roughness^2; no cosine factor; srgb2lin on constants).
+// FP32 throughout: the reference's stray double literals ("4.0 *", "1.0 /") round to the same
+// floats as the single-precision expressions used here.
+#pragma once
+#include "mox_structs.h"
+#include "rng.cuh"
+
+MOX_D float fresnelDielectric(float cosI, float cosT, float ior) {
+  float rs = (cosI - cosT * ior) / (cosI + ior * cosT);
+  float rp = (cosI * ior - cosT) / (cosI * ior + cosT);
+  return 0.5f * (rs * rs + rp * rp);
+}
+
+// Integer-ULP offset along the normal, per coordinate.
+MOX_D float offsetCoord(float h, float n) {
+  const float epsilon = 1.0e-4f;
+  if ((__float_as_int(h) & 0x7fffffff) < __float_as_int(epsilon)) return h + epsilon * n;
+  return __int_as_float(__float_as_int(h) + (int)(copysignf(8192.0f, h) * n));
+}
+MOX_D float3 offsetPoint(const float3& p, const float3& n) {
+  return mk3(offsetCoord(p.x, n.x), offsetCoord(p.y, n.y), offsetCoord(p.z, n.z));
+}
+// Re-project the hit onto the triangle plane through p0, then push it to both sides.
+MOX_D void refineHitpoint(const float3& hitPoint, const float3& dir, const float3& normal, const float3& p0,
+                          float3& back, float3& front) {
+  float refinedT = -(dot(normal, hitPoint - p0)) / dot(normal, dir);
+  float3 refined = hitPoint + refinedT * dir;
+  if (dot(dir, normal) > 0.0f) { back = offsetPoint(refined, normal); front = offsetPoint(refined, -normal); }
+  else { back = offsetPoint(refined, -normal); front = offsetPoint(refined, normal); }
+}
+
+MOX_D float sqr(float x) { return x * x; }
+MOX_D float GTR1(float NdotH, float a) {
+  if (a >= 1.f) return 1.f / MOX_PI_F;
+  float a2 = a * a;
+  float t = 1.f + (a2 - 1.f) * NdotH * NdotH;
+  return (a2 - 1.0f) / (MOX_PI_F * logf(a2) * t);
+}
+MOX_D float GTR2(float NdotH, float a) {
+  float a2 = a * a;
+  float t = 1.f + (a2 - 1.f) * NdotH * NdotH;
+  return a2 / (MOX_PI_F * t * t);
+}
+MOX_D float GTR2Aniso(float NdotH, float HdotX, float HdotY, float ax, float ay) {
+  return 1 / (MOX_PI_F * ax * ay * sqr(sqr(HdotX / ax) + sqr(HdotY / ay) + NdotH * NdotH));
+}
+MOX_D float schlickFresnel(float u) {
+  float m = clampf(1.f - u, 0.f, 1.f);
+  float m2 = m * m;
+  return m2 * m2 * m;
+}
+MOX_D float smithGGgx(float NdotV, float alphaG) {
+  float a = alphaG * alphaG, b = NdotV * NdotV;
+  return 1.f / (NdotV + sqrtf(a + b - a * b));
+}
+MOX_D float smithGGgxAniso(float NdotV, float VdotX, float VdotY, float ax, float ay) {
+  return 1.0f / (NdotV + sqrtf(sqr(VdotX * ax) + sqr(VdotY * ay) + sqr(NdotV)));
+}
+MOX_D float powerHeuristic(float a, float b) { float t = a * a; return t / (b * b + t); }
+
+// disney.h:9-30; draws: lobe, then (u1,u2) | (phi, xi).
+MOX_D void disneySample(Rng& rng, const DisneyParams& mp, const float3& N, float3& L, const float3& V, float3& H) {
+  float diffuseRatio = 0.5f * (1.0f - mp.metallic);
+  Onb3 onb(N);
+  float r0 = rng.rnd();
+  if (r0 < diffuseRatio) {
+    float u1 = rng.rnd(), u2 = rng.rnd();
+    float r = sqrtf(u1), phi = 2.0f * MOX_PI_F * u2;
+    float3 p;
+    p.x = r * cosf(phi);
+    p.y = r * sinf(phi);
+    p.z = sqrtf(fmaxf(0.0f, 1.0f - p.x * p.x - p.y * p.y));
+    L = normalize(onb.toWorld(p));
+    H = normalize(L + V);
+  } else {
+    float a = fmaxf(0.001f, mp.roughness);
+    float phi = rng.rnd() * 2.0f * MOX_PI_F;
+    float xi = rng.rnd();
+    float cosTheta = sqrtf((1.f - xi) / (1.0f + (a * a - 1.f) * xi));
+    float sinTheta = sqrtf(1.0f - (cosTheta * cosTheta));
+    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    H = onb.toWorld(mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));
+    L = normalize(2.0f * dot(V, H) * H - V);
+    H = normalize(H);
+  }
+}
+
+MOX_D float disneyPdf(const DisneyParams& mp, const float3& N, const float3& L, const float3& H) {
+  float diffuseRatio = 0.5f * (1.0f - mp.metallic);
+  float specularAlpha = fmaxf(0.001f, mp.roughness);
+  float clearcoatAlpha = lerpf(0.1f, 0.001f, mp.clearcoatGloss);
+  float specularRatio = 1.f - diffuseRatio;
+  float cosTheta = fabsf(dot(N, H));
+  float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha) * cosTheta;
+  float pdfGTR2 = GTR2(cosTheta, specularAlpha) * cosTheta;
+  float ratio = 1.0f / (1.0f + mp.clearcoat);
+  float pdfH = lerpf(pdfGTR1, pdfGTR2, ratio);
+  float pdfL = pdfH / (4.0f * fabsf(dot(L, H)));
+  float pdfDiff = fabsf(dot(N, L)) / MOX_PI_F;
+  return diffuseRatio * pdfDiff + specularRatio * pdfL;
+}
+
+MOX_D float3 disneyEval(const DisneyParams& mp, const float3& baseColor, const float3& N, const float3& L,
+                        const float3& V, const float3& H) {
+  Onb3 onb(N);
+  float NdotL = dot(N, L), NdotV = dot(N, V), NdotH = dot(N, H), LdotH = dot(L, H);
+  float3 Cdlin = mk3(powf(baseColor.x, 2.2f), powf(baseColor.y, 2.2f), powf(baseColor.z, 2.2f));
+  float Cdlum = dot(Cdlin, mk3(0.3f, 0.6f, 0.1f));
+  float3 Ctint = Cdlum > 0.f ? Cdlin / Cdlum : mk3(1.f);
+  float3 Cspec0 = lerp3(mp.specular * 0.08f * lerp3(mk3(1.f), Ctint, mp.specularTint), Cdlin, mp.metallic);
+  float3 Csheen = lerp3(mk3(1.f), Ctint, mp.sheenTint);
+  float FL = schlickFresnel(NdotL), FV = schlickFresnel(NdotV);
+  float Fd90 = 0.5f + 2.f * LdotH * LdotH * mp.roughness;
+  float Fd = lerpf(1.f, Fd90, FL) * lerpf(1.f, Fd90, FV);
+  float Fss90 = LdotH * LdotH * mp.roughness;
+  float Fss = lerpf(1.0f, Fss90, FL) * lerpf(1.0f, Fss90, FV);
+  float ss = 1.25f * (Fss * (1.f / (NdotL + NdotV) - 0.5f) + 0.5f);
+  float aspect = sqrtf(1 - mp.anisotropic * 0.9f);
+  float ax = fmaxf(.001f, sqr(mp.roughness) / aspect);
+  float ay = fmaxf(.001f, sqr(mp.roughness) * aspect);
+  float3 X = normalize(onb.tangent);
+  float3 Y = normalize(cross(N, X));
+  float Ds = GTR2Aniso(NdotH, dot(H, X), dot(H, Y), ax, ay);
+  float FH = schlickFresnel(LdotH);
+  float3 Fs = lerp3(Cspec0, mk3(1.f), FH);
+  float Gs = smithGGgxAniso(NdotL, dot(L, X), dot(L, Y), ax, ay) * smithGGgxAniso(NdotV, dot(V, X), dot(V, Y), ax, ay);
+  float3 Fsheen = FH * mp.sheen * Csheen;
+  float Dr = GTR1(NdotH, lerpf(0.1f, 0.001f, mp.clearcoatGloss));
+  float Fr = lerpf(0.04f, 1.f, FH);
+  float Gr = smithGGgx(NdotL, 0.25f) * smithGGgx(NdotV, 0.25f);
+  return ((1.0f / MOX_PI_F) * lerpf(Fd, ss, mp.subsurface) * Cdlin + Fsheen) * (1.0f - mp.metallic) + Gs * Fs * Ds +
+         mk3(0.25f * mp.clearcoat * Gr * Fr * Dr);
+}

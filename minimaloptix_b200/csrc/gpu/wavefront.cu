@@ -1,0 +1,450 @@
+// wavefront.cu — the render kernels.  The reference is a recursive OptiX megakernel
+// (camera() -> rtTrace -> closest-hit program -> rtTrace ...); here one sample of every pixel
+// is a path in a wavefront, advanced one bounce per iteration:
+//
+//   k_generate   camera()                      Camera.cu:21-36
+//   k_extend     rtTrace closest hit + miss (miss.cu:10-12) + light() (Material.cu:238-240)
+//                + the depth test every scattering program starts with (Material.cu:29,50,73,119);
+//                surviving paths are binned into per-material queues
+//   k_shade_*    lambertian / metal / glass / disney   Material.cu:28-223, disney.h
+//   k_shadow     shadow rtTrace + disneyAnyHit         Material.cu:189-203, 225-232
+//   k_apply      adds the NEE terms to the path radiance in light order (deterministic)
+//   k_accumulate clamp + accuBuffer +=                 Camera.cu:39-41
+//
+// Every reference program is affine in the child radiance (colour = A * child + B), so a path
+// carries throughput T and radiance R: R += T*B, T *= A.
+#include "wavefront.h"
+
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ uint32_t queuePush(uint32_t* counter) {
+  // warp-aggregated atomic increment
+  uint32_t mask = __activemask();
+  int leader = __ffs(mask) - 1;
+  int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+struct PathCtx {
+  uint32_t path, pixel;
+  int32_t launchSeed;
+};
+
+__device__ __forceinline__ PathCtx pathCtx(const LaunchCtx& c, uint32_t path) {
+  PathCtx p;
+  p.path = path;
+  uint32_t s = path / c.nOwned, j = path - s * c.nOwned;
+  p.pixel = __ldg(&c.ownedPix[j]);
+  p.launchSeed = __ldg(&c.pb.seeds[s]);
+  return p;
+}
+
+// ------------------------------------------------------------------ generate (Camera.cu:21-36)
+__global__ void __launch_bounds__(TPB) k_generate(LaunchCtx c, uint32_t nPaths) {
+  uint32_t p = blockIdx.x * TPB + threadIdx.x;
+  if (p >= nPaths) return;
+  PathCtx pc = pathCtx(c, p);
+  const RenderParams& rp = c.rp;
+  uint32_t x = pc.pixel % rp.W, y = pc.pixel / rp.W;
+  int st = rp.rngMode == 0 ? (int)tea16(pc.pixel, (uint32_t)pc.launchSeed) : 0;
+  Rng rng = makeRng(rp.rngMode, st, pc.pixel, (uint32_t)pc.launchSeed, 1u);
+  const CamParams& cp = rp.cam;
+  float3 lens = cp.lensRadius * randInUnitDisk(rng);
+  float3 offset = f3(cp.u) * lens.x + f3(cp.v) * lens.y;
+  float r1 = rng.rnd();
+  float r2 = rng.rnd();
+  float sx = ((float)x + r1 - 0.5f) / (float)rp.W;
+  float sy = ((float)y + r2 - 0.5f) / (float)rp.H;
+  float3 o = f3(cp.origin) + offset;
+  float3 d = normalize(f3(cp.scrLowerLeftCorner) + sx * f3(cp.horizontal) + sy * f3(cp.vertical) - f3(cp.origin) - offset);
+  c.pb.rayO[p] = make_float4(o.x, o.y, o.z, rp.eps);
+  c.pb.rayD[p] = make_float4(d.x, d.y, d.z, MOX_RAY_TMAX);
+  c.pb.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
+  c.pb.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  c.pb.state[p] = rng.state;
+  c.pb.qCur[p] = p;
+}
+
+// ------------------------------------------------------------------ extend + classify
+template <bool COUNT>
+__global__ void __launch_bounds__(TPB) k_extend(LaunchCtx c, const uint32_t* __restrict__ queue, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= count) return;
+  uint32_t path = queue[i];
+  float4 ro = c.pb.rayO[path], rd = c.pb.rayD[path];
+  uint32_t nv = 0, np = 0;
+  Hit h = traceClosest<COUNT>(c.scene, mk3(ro), mk3(rd), ro.w, rd.w, &nv, &np);
+  if (COUNT) {
+    // 64-bit totals kept as two words; one atomic per warp would be nicer, this is the counting build only
+    atomicAdd((unsigned long long*)(c.pb.counters + C_NODEVIS_LO), (unsigned long long)nv);
+    atomicAdd((unsigned long long*)(c.pb.counters + C_PRIMTEST_LO), (unsigned long long)np);
+  }
+  const RenderParams& rp = c.rp;
+  if (h.prim < 0) {  // miss: payload colour (1,1,1) * bgColor
+    float4 T = c.pb.thr[path], R = c.pb.rad[path];
+    float3 r = mk3(R) + mk3(T) * (mk3(1.f) * rp.bg);
+    c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
+    return;
+  }
+  PrimDesc pd = c.scene.prims[h.prim];
+  const GpuMaterial* m = c.scene.mats + (pd.typeMat >> 2);
+  int kind = __ldg(&m->kind);
+  if (kind == MOX_MAT_LIGHT) {
+    float4 T = c.pb.thr[path], R = c.pb.rad[path];
+    float3 r = mk3(R) + mk3(T) * f3(m->lgt.emission);
+    c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
+    return;
+  }
+  // incoming payload colour is always (1,1,1): |colour| = sqrt(3)
+  if (depth > rp.maxDepth || length(mk3(1.f)) < rp.minIntensity) {
+    float4 T = c.pb.thr[path], R = c.pb.rad[path];
+    float3 r = mk3(R) + mk3(T) * rp.absorb;
+    c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
+    return;
+  }
+  c.pb.hit[path] = make_float4(h.t, __int_as_float(h.prim), h.beta, h.gamma);
+  int q = kind == MOX_MAT_LAMBERTIAN ? Q_LAMBERT
+        : kind == MOX_MAT_METAL ? Q_METAL
+        : kind == MOX_MAT_GLASS ? Q_DIELECTRIC
+        : (m->dis.brdfType == GLASS ? Q_DIELECTRIC : Q_DISNEY);
+  // one warp-aggregated push per queue present in the warp
+  for (int k = 0; k < Q_COUNT; ++k) {
+    if (q == k) {
+      uint32_t pos = queuePush(c.pb.counters + C_MAT0 + k);
+      c.pb.qMat[k][pos] = path;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ hit attributes (Geometry.cu)
+struct Attr { float3 Ng, Ns, front, back, hitPoint; float u, v; };
+
+__device__ __forceinline__ float3 ld3(const float* p, int i) { return mk3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
+
+__device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc& pd, const float3& o, const float3& d,
+                                               float t, float beta, float gamma, bool needShading) {
+  Attr a;
+  uint32_t type = pd.typeMat & 3u;
+  a.hitPoint = o + t * d;
+  a.u = a.v = 0.f;
+  if (type == PT_SPHERE) {
+    float4 cr = __ldg(&s.analytic[pd.geom].a);
+    a.Ng = normalize(o + t * d - mk3(cr));
+    a.Ns = a.Ng;
+    a.front = a.back = a.hitPoint;
+  } else if (type == PT_QUAD) {
+    a.Ng = mk3(__ldg(&s.analytic[pd.geom].a));
+    a.Ns = a.Ng;
+    a.front = a.back = a.hitPoint;
+  } else {
+    const TriIdx* ti = s.tris + pd.geom;
+    int v0 = __ldg(&ti->v[0]), v1 = __ldg(&ti->v[1]), v2 = __ldg(&ti->v[2]);
+    float3 p0 = ld3(s.verts, v0), p1 = ld3(s.verts, v1), p2 = ld3(s.verts, v2);
+    float3 e0 = p1 - p0, e1 = p0 - p2;
+    a.Ng = normalize(cross(e1, e0));
+    a.Ns = a.Ng;
+    a.front = a.back = a.hitPoint;
+    if (needShading) {
+      int n0 = __ldg(&ti->n[0]);
+      if (n0 >= 0) {
+        int n1 = __ldg(&ti->n[1]), n2 = __ldg(&ti->n[2]);
+        a.Ns = normalize(ld3(s.normals, n1) * beta + ld3(s.normals, n2) * gamma + ld3(s.normals, n0) * (1.f - beta - gamma));
+      }
+      int t0 = __ldg(&ti->t[0]);
+      if (t0 >= 0) {
+        int t1 = __ldg(&ti->t[1]), t2 = __ldg(&ti->t[2]);
+        float w = 1.0f - beta - gamma;
+        a.u = __ldg(s.uvs + 2 * t1) * beta + __ldg(s.uvs + 2 * t2) * gamma + __ldg(s.uvs + 2 * t0) * w;
+        a.v = __ldg(s.uvs + 2 * t1 + 1) * beta + __ldg(s.uvs + 2 * t2 + 1) * gamma + __ldg(s.uvs + 2 * t0 + 1) * w;
+      }
+      refineHitpoint(a.hitPoint, d, a.Ng, p0, a.back, a.front);
+    }
+  }
+  return a;
+}
+
+struct ShadeIn {
+  uint32_t path;
+  float3 o, d;
+  float t, beta, gamma;
+  PrimDesc pd;
+  const GpuMaterial* m;
+  Rng rng;
+};
+
+__device__ __forceinline__ ShadeIn loadShadeIn(const LaunchCtx& c, uint32_t path, uint32_t depth) {
+  ShadeIn s;
+  s.path = path;
+  float4 ro = c.pb.rayO[path], rd = c.pb.rayD[path], h = c.pb.hit[path];
+  s.o = mk3(ro); s.d = mk3(rd);
+  s.t = h.x; s.beta = h.z; s.gamma = h.w;
+  s.pd = c.scene.prims[__float_as_int(h.y)];
+  s.m = c.scene.mats + (s.pd.typeMat >> 2);
+  PathCtx pc = pathCtx(c, path);
+  s.rng = makeRng(c.rp.rngMode, c.pb.state[path], pc.pixel, (uint32_t)pc.launchSeed, depth);
+  return s;
+}
+
+__device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const float3& o, const float3& d, const float3& A,
+                                      int childState) {
+  c.pb.rayO[path] = make_float4(o.x, o.y, o.z, c.rp.eps);
+  c.pb.rayD[path] = make_float4(d.x, d.y, d.z, MOX_RAY_TMAX);
+  float4 T = c.pb.thr[path];
+  float3 t = mk3(T) * A;
+  c.pb.thr[path] = make_float4(t.x, t.y, t.z, 0.f);
+  c.pb.state[path] = childState;
+  uint32_t pos = queuePush(c.pb.counters + C_NEXT);
+  c.pb.qNext[pos] = path;
+}
+
+// lambertian (Material.cu:28-43) and metal (:49-66)
+template <bool METAL>
+__global__ void __launch_bounds__(TPB) k_shade_diffuse(LaunchCtx c, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= count) return;
+  ShadeIn s = loadShadeIn(c, c.pb.qMat[METAL ? Q_METAL : Q_LAMBERT][i], depth);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, false);
+  float3 v = randInUnitSphere(s.rng);
+  float3 dir, albedo;
+  if (METAL) {
+    dir = normalize(reflect3(s.d, a.Ng) + s.m->met.fuzz * v);
+    albedo = f3(s.m->met.albedo);
+  } else {
+    dir = normalize(a.Ng + v);
+    albedo = f3(s.m->lam.albedo);
+  }
+  spawn(c, s.path, a.hitPoint, dir, albedo, s.rng.forkState((int)depth + 1));
+}
+
+// glass (Material.cu:72-110) and disney/GLASS (:134-168)
+__global__ void __launch_bounds__(TPB) k_shade_dielectric(LaunchCtx c, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= count) return;
+  ShadeIn s = loadShadeIn(c, c.pb.qMat[Q_DIELECTRIC][i], depth);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, true);
+  float ior;
+  float3 tint;
+  if (s.m->kind == MOX_MAT_GLASS) { ior = s.m->gls.refIdx; tint = f3(s.m->gls.albedo); }
+  else { ior = 1.45f; tint = f3(s.m->dis.color); }
+  float3 normal = a.Ns;
+  float cosI = -dot(s.d, normal);
+  float refIdx;
+  if (cosI > 0.f) { refIdx = ior; }
+  else { refIdx = 1.f / ior; cosI = -cosI; normal = -normal; }
+  float3 refracted;
+  bool tir = !refract3(refracted, s.d, normal, refIdx);
+  float cosT = -dot(normal, refracted);
+  float reflectProb = tir ? 1.f : fresnelDielectric(cosI, cosT, refIdx);
+  int childState = s.rng.forkState((int)depth + 1);  // forked BEFORE the coin flip (Material.cu:100-101)
+  float3 o, dir;
+  if (s.rng.rnd() < reflectProb) { o = a.front; dir = reflect3(s.d, normal); }
+  else { o = a.back; dir = refracted; }
+  spawn(c, s.path, o, dir, tint, childState);
+}
+
+// disney/NORMAL (Material.cu:170-222)
+__global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= count) return;
+  ShadeIn s = loadShadeIn(c, c.pb.qMat[Q_DISNEY][i], depth);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, true);
+  const DisneyParams dp = s.m->dis;
+  float3 N = faceforward3(a.Ns, -s.d, a.Ng);
+  float3 V = -s.d;
+  float3 baseColor = f3(dp.color);
+  float3 Tprev = mk3(c.pb.thr[s.path]);
+  float3 L, H;
+  const int nL = c.scene.nLights;
+  uint32_t shadowCount = 0;
+  for (int li = 0; li < nL; ++li) {
+    const LightParams* lp = c.scene.lights + li;
+    float3 lpos = mk3(__ldg(&lp->position.x), __ldg(&lp->position.y), __ldg(&lp->position.z));
+    float3 pointOnLight, normalOnLight;
+    if (__ldg((const int*)&lp->shape) == SPHERE) {
+      pointOnLight = lpos + randInUnitSphere(s.rng) * __ldg(&lp->radius);
+      normalOnLight = normalize(pointOnLight - lpos);
+    } else {
+      float r1 = s.rng.rnd();
+      float r2 = s.rng.rnd();
+      pointOnLight = lpos + f3(lp->u) * r1 + f3(lp->v) * r2;
+      normalOnLight = normalize(f3(lp->normal));
+    }
+    L = pointOnLight - a.front;
+    float lightDst = length(L);
+    L = normalize(L);
+    size_t slot = (size_t)i * nL + li;
+    float3 contrib = mk3(0.f);
+    float active = 0.f;
+    if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
+      active = 1.f;
+      shadowCount++;
+      H = normalize(L + V);
+      float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
+      float objPdf = disneyPdf(dp, N, L, H);
+      if (lightPdf > 0 && objPdf > 0) {
+        float3 brdf = disneyEval(dp, baseColor, N, L, V, H);
+        contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
+      }
+    }
+    float3 pc = Tprev * contrib;
+    c.pb.shO[slot] = make_float4(a.front.x, a.front.y, a.front.z, lightDst - c.rp.eps);
+    c.pb.shD[slot] = make_float4(L.x, L.y, L.z, active);
+    c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
+  }
+  if (shadowCount) atomicAdd(c.pb.counters + C_SHADOW, shadowCount);
+  {  // + emission
+    float3 e = f3(dp.emission);
+    if (e.x != 0.f || e.y != 0.f || e.z != 0.f) {
+      float3 r = mk3(c.pb.rad[s.path]) + Tprev * e;
+      c.pb.rad[s.path] = make_float4(r.x, r.y, r.z, 0.f);
+    }
+  }
+  disneySample(s.rng, dp, N, L, V, H);
+  if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
+    float pdf = disneyPdf(dp, N, L, H);
+    if (pdf > 0) {
+      float3 brdf = disneyEval(dp, baseColor, N, L, V, H);
+      spawn(c, s.path, a.front, L, brdf / pdf, s.rng.forkState((int)depth + 1));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_shadow(LaunchCtx c, uint32_t nSlots) {
+  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= nSlots) return;
+  float4 d = c.pb.shD[i];
+  if (d.w == 0.f) return;
+  float4 o = c.pb.shO[i];
+  float4 col = c.pb.shC[i];
+  if (col.x == 0.f && col.y == 0.f && col.z == 0.f) return;
+  float3 atten = traceShadow(c.scene, mk3(o), mk3(d), c.rp.eps, o.w);
+  float3 r = mk3(col) * atten;
+  c.pb.shC[i] = make_float4(r.x, r.y, r.z, 0.f);
+}
+
+__global__ void __launch_bounds__(TPB) k_apply(LaunchCtx c, uint32_t count) {
+  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= count) return;
+  uint32_t path = c.pb.qMat[Q_DISNEY][i];
+  const int nL = c.scene.nLights;
+  float3 direct = mk3(0.f);
+  for (int li = 0; li < nL; ++li) direct += mk3(c.pb.shC[(size_t)i * nL + li]);
+  float3 r = mk3(c.pb.rad[path]) + direct;
+  c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
+}
+
+// Camera.cu:39-41 — samples of one pixel are added in launch order, so a batch of S samples
+// gives bit-identical sums to S successive launches.
+__global__ void __launch_bounds__(TPB) k_accumulate(LaunchCtx c, uint32_t nSamples) {
+  uint32_t j = blockIdx.x * TPB + threadIdx.x;
+  if (j >= c.nOwned) return;
+  uint32_t pix = c.ownedPix[j];
+  float* a = c.accu + 3 * (size_t)pix;
+  float3 acc = mk3(a[0], a[1], a[2]);
+  uint32_t bad = 0;
+  for (uint32_t s = 0; s < nSamples; ++s) {
+    float4 r = c.pb.rad[(size_t)s * c.nOwned + j];
+    if (!isfinite(r.x) || !isfinite(r.y) || !isfinite(r.z)) bad++;
+    acc.x += clampf(r.x, 0.f, 1.f);
+    acc.y += clampf(r.y, 0.f, 1.f);
+    acc.z += clampf(r.z, 0.f, 1.f);
+  }
+  a[0] = acc.x; a[1] = acc.y; a[2] = acc.z;
+  if (bad) atomicAdd(c.pb.counters + C_NONFINITE, bad);
+}
+
+// ------------------------------------------------------------------ raw ray queries
+template <bool COUNT>
+__global__ void __launch_bounds__(TPB) k_trace_closest(SceneView s, const float4* __restrict__ rays, size_t n,
+                                                        float4* __restrict__ hits, uint32_t* counters) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+  uint32_t nv = 0, np = 0;
+  Hit h = traceClosest<COUNT>(s, mk3(ro), mk3(rd), ro.w, rd.w, &nv, &np);
+  hits[i] = make_float4(h.t, __int_as_float(h.prim), h.beta, h.gamma);
+  if (COUNT) {
+    atomicAdd((unsigned long long*)(counters + C_NODEVIS_LO), (unsigned long long)nv);
+    atomicAdd((unsigned long long*)(counters + C_PRIMTEST_LO), (unsigned long long)np);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_trace_shadow(SceneView s, const float4* __restrict__ rays, size_t n, float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+  float3 a = traceShadow(s, mk3(ro), mk3(rd), ro.w, rd.w);
+  out[3 * i] = a.x; out[3 * i + 1] = a.y; out[3 * i + 2] = a.z;
+}
+
+__global__ void k_pack_owned(const float* __restrict__ accu, const uint32_t* __restrict__ ownedPix, uint32_t nOwned, float* __restrict__ dst) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nOwned) return;
+  uint32_t pix = ownedPix[j];
+  dst[3 * (size_t)j] = accu[3 * (size_t)pix];
+  dst[3 * (size_t)j + 1] = accu[3 * (size_t)pix + 1];
+  dst[3 * (size_t)j + 2] = accu[3 * (size_t)pix + 2];
+}
+__global__ void k_unpack_owned(float* __restrict__ accu, const uint32_t* __restrict__ ownedPix, uint32_t nOwned, const float* __restrict__ src) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nOwned) return;
+  uint32_t pix = ownedPix[j];
+  accu[3 * (size_t)pix] = src[3 * (size_t)j];
+  accu[3 * (size_t)pix + 1] = src[3 * (size_t)j + 1];
+  accu[3 * (size_t)pix + 2] = src[3 * (size_t)j + 2];
+}
+
+inline unsigned grid(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
+
+}  // namespace
+
+void launchGenerate(const LaunchCtx& c, uint32_t nSamples) {
+  uint32_t n = nSamples * c.nOwned;
+  if (n) k_generate<<<grid(n), TPB, 0, c.stream>>>(c, n);
+}
+void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
+  if (!count) return;
+  if (c.countTraversal) k_extend<true><<<grid(count), TPB, 0, c.stream>>>(c, queue, count, depth);
+  else k_extend<false><<<grid(count), TPB, 0, c.stream>>>(c, queue, count, depth);
+}
+void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
+  if (!count) return;
+  switch (kind) {
+    case Q_LAMBERT: k_shade_diffuse<false><<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
+    case Q_METAL: k_shade_diffuse<true><<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
+    case Q_DIELECTRIC: k_shade_dielectric<<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
+    case Q_DISNEY: k_shade_disney<<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
+  }
+}
+void launchShadowAndApply(const LaunchCtx& c, uint32_t disneyCount) {
+  if (!disneyCount || c.scene.nLights == 0) return;
+  size_t slots = (size_t)disneyCount * c.scene.nLights;
+  k_shadow<<<grid(slots), TPB, 0, c.stream>>>(c, (uint32_t)slots);
+  k_apply<<<grid(disneyCount), TPB, 0, c.stream>>>(c, disneyCount);
+}
+void launchAccumulate(const LaunchCtx& c, uint32_t nSamples) {
+  if (c.nOwned) k_accumulate<<<grid(c.nOwned), TPB, 0, c.stream>>>(c, nSamples);
+}
+void launchTraceClosest(const SceneView& s, const float4* rays, size_t n, float4* hits, bool count, uint32_t* counters,
+                        cudaStream_t stream) {
+  if (!n) return;
+  if (count) k_trace_closest<true><<<grid(n), TPB, 0, stream>>>(s, rays, n, hits, counters);
+  else k_trace_closest<false><<<grid(n), TPB, 0, stream>>>(s, rays, n, hits, counters);
+}
+void launchTraceShadow(const SceneView& s, const float4* rays, size_t n, float* out, cudaStream_t stream) {
+  if (n) k_trace_shadow<<<grid(n), TPB, 0, stream>>>(s, rays, n, out);
+}
+void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream) {
+  if (nOwned) k_pack_owned<<<grid(nOwned), TPB, 0, stream>>>(accu, ownedPix, nOwned, dst);
+}
+void launchUnpackOwned(float* accu, const uint32_t* ownedPix, uint32_t nOwned, const float* src, cudaStream_t stream) {
+  if (nOwned) k_unpack_owned<<<grid(nOwned), TPB, 0, stream>>>(accu, ownedPix, nOwned, src);
+}

@@ -1,0 +1,48 @@
+// wavefront.h — device buffers and launchers of the wavefront integrator.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "gpu_types.h"
+
+// Material queues built by the extend kernel.
+enum ShadeQueue { Q_LAMBERT = 0, Q_METAL = 1, Q_DIELECTRIC = 2, Q_DISNEY = 3, Q_COUNT = 4 };
+
+// Device counters (uint32 words).
+enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
+                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_WORDS = 16 };
+
+struct PathBuffers {
+  size_t capacity = 0;      // paths
+  size_t shadowSlots = 0;   // capacity * nLights
+  float4 *rayO = nullptr, *rayD = nullptr, *hit = nullptr, *thr = nullptr, *rad = nullptr;
+  int* state = nullptr;
+  uint32_t *qCur = nullptr, *qNext = nullptr;
+  uint32_t* qMat[Q_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+  float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;
+  uint32_t* counters = nullptr;   // C_WORDS
+  int32_t* seeds = nullptr;       // launch seed per sample of the batch
+  size_t seedCap = 0;
+};
+
+struct LaunchCtx {
+  SceneView scene;
+  RenderParams rp;
+  PathBuffers pb;
+  const uint32_t* ownedPix;  // device
+  uint32_t nOwned;
+  float* accu;               // device W*H*3
+  bool countTraversal;
+  cudaStream_t stream;
+};
+
+void launchGenerate(const LaunchCtx& c, uint32_t nSamples);
+void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth);
+void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth);
+void launchShadowAndApply(const LaunchCtx& c, uint32_t disneyCount);
+void launchAccumulate(const LaunchCtx& c, uint32_t nSamples);
+void launchTraceClosest(const SceneView& s, const float4* rays, size_t n, float4* hits, bool count, uint32_t* counters,
+                        cudaStream_t stream);
+void launchTraceShadow(const SceneView& s, const float4* rays, size_t n, float* out, cudaStream_t stream);
+void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream);
+void launchUnpackOwned(float* accu, const uint32_t* ownedPix, uint32_t nOwned, const float* src, cudaStream_t stream);

@@ -70,7 +70,10 @@ class Stats(C.Structure):
                 ("prim_tests", C.c_uint64), ("ms_render", C.c_double), ("ms_build", C.c_double),
                 ("n_prims", C.c_uint32), ("n_triangles", C.c_uint32), ("n_spheres", C.c_uint32),
                 ("n_quads", C.c_uint32), ("n_nodes", C.c_uint32), ("node_bytes", C.c_uint32),
-                ("prim_bytes", C.c_uint32), ("n_lights", C.c_uint32)]
+                ("prim_bytes", C.c_uint32), ("n_lights", C.c_uint32),
+                ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double),
+                ("ms_shadow", C.c_double), ("ms_accumulate", C.c_double), ("extend_launches", C.c_uint64),
+                ("kernel_launches", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
