@@ -1,0 +1,203 @@
+"""Host-side tests (no GPU): scene description loader, OBJ reader, parameter builders, image
+output.  Golden values in tests/golden/loader.json were produced by the REFERENCE's own
+scene.cpp + tiny_obj_loader.h (scripts/make_loader_golden.py); the coffee scene files live under
+scenes/coffee/ (copied from the reference by scripts/fetch_reference_scenes.py, git-ignored)."""
+import ctypes as C
+import json
+import math
+import os
+import struct
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from minimaloptix_b200 import structs as S
+
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "loader.json")))
+COFFEE = os.path.join(ROOT, "scenes", "coffee")
+have_coffee = os.path.exists(os.path.join(COFFEE, "coffee.scene"))
+
+
+def test_parse_double_matches_reference_bits(host):
+    for text, ok, bits in GOLD["parse_double"]:
+        got = host.parse_double(text)
+        assert (got is not None) == bool(ok), text
+        if ok:
+            assert struct.pack("<d", got).hex() == bits, text
+
+
+def _obj_scene(host, tmpdir, obj_path):
+    """Wrap a lone OBJ into a one-mesh .scene so it goes through loadSceneFile."""
+    name = "t"
+    d = os.path.join(tmpdir, name)
+    os.makedirs(d, exist_ok=True)
+    dst = os.path.join(d, "m.obj")
+    with open(obj_path, "rb") as f, open(dst, "wb") as g:
+        g.write(f.read())
+    with open(os.path.join(d, name + ".scene"), "w") as f:
+        f.write("material M\n{\n\tcolor 1 1 1\n}\nmesh\n{\n\tfile m.obj\n\tmaterial M\n}\n")
+    return host.Scene.load(d, name)
+
+
+@pytest.mark.parametrize("name", ["ngons.obj", "numbers.obj"])
+def test_obj_fixtures_match_reference_tinyobj(host, name):
+    want = GOLD["obj"]["golden/" + name]
+    with tempfile.TemporaryDirectory() as tmp:
+        sc = _obj_scene(host, tmp, os.path.join(ROOT, "tests", "golden", "obj", name))
+        info = sc.info()
+        assert info.n_meshes == want["shapes"]
+        for s in range(want["shapes"]):
+            mi = sc.mesh_info(s)
+            h = sc.mesh_hash(s)
+            assert mi["faces"] == want["faces"][s]
+            assert (mi["vertices"], mi["normals"], mi["texcoords"]) == (want["vertices"], want["normals"], want["texcoords"])
+            assert [hex(x) for x in h[:3]] == want["attr_hash"]
+            assert hex(h[3]) == want["index_hash"][s], (name, s)
+
+
+@pytest.mark.skipif(not have_coffee, reason="scenes/coffee not fetched")
+def test_coffee_scene_matches_reference_loader(host):
+    want = GOLD["coffee_scene"]
+    sc = host.Scene.load(COFFEE, "coffee")
+    info = sc.info()
+    # Mesh010.obj (the glass carafe) is a missing large blob upstream: skipped with a warning
+    present = [n for n in want["mesh_names"] if os.path.exists(os.path.join(COFFEE, n))]
+    assert len(want["mesh_names"]) == 20 and len(present) == 19
+    assert info.n_meshes == 19 and info.n_warnings == 1 and "Mesh010.obj" in sc.warnings()[0]
+    assert info.n_lights == want["lights"] == 3
+    assert info.n_triangles == 168193 and info.n_vertices == 101812
+    assert np.allclose(list(info.aabb_min), [-1, 0, -1.09417], atol=1e-5)
+    assert np.allclose(list(info.aabb_max), [1, 0.811135, 1], atol=1e-5)
+    # materials, in mesh order, byte for byte (DisneyParams, 72 bytes)
+    k = 0
+    for i, name in enumerate(want["mesh_names"]):
+        if name not in present:
+            continue
+        mi = sc.mesh_info(k)
+        assert mi["name"].startswith(name)
+        assert bytes(mi["disney"]).hex() == want["material_bytes"][i], name
+        g = GOLD["obj"]["coffee/" + name]
+        assert mi["faces"] == g["faces"][0] and mi["vertices"] == g["vertices"]
+        h = sc.mesh_hash(k)
+        assert [hex(x) for x in h[:3]] == g["attr_hash"], name   # vertex / normal / texcoord bits
+        assert hex(h[3]) == g["index_hash"][0], name
+        k += 1
+    for i in range(3):
+        assert bytes(sc.light(i)).hex() == want["light_bytes"][i]
+    # camera of SCENE_COFFEE (MinimalOptiX.cpp:258-270): from = (0, .22 ext.y, .25 ext.z), at = from + (0, -.01875, -1)
+    ext = np.array(list(info.aabb_max)) - np.array(list(info.aabb_min))
+    assert np.allclose(list(info.look_from), [0, 0.22 * ext[1], 0.25 * ext[2]], atol=1e-6)
+    assert np.allclose(np.array(list(info.look_at)) - np.array(list(info.look_from)), [0, -0.01875, -1], atol=1e-6)
+    assert info.vfov == 45 and info.aperture == 0 and list(info.bg) == [0, 0, 0]
+
+
+def test_scene_grammar_quirks(host):
+    """Substring block detection, comments at column 0 only, defaults, brdf %i, Quad/Sphere lights."""
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "q")
+        os.makedirs(d)
+        with open(os.path.join(d, "tri.obj"), "w") as f:
+            f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+        with open(os.path.join(d, "q.scene"), "w") as f:
+            f.write("# comment\nproperties\n{\n\twidth 640\n\theight 480\n}\n"
+                    "material Shiny\n{\n\tcolor 0.25 0.5 0.75\n\tmetallic 1.0\n\tspecularTint 0.3\n\tbrdf 0x1\n\troughness 0.125\n}\n"
+                    "mesh\n{\n\tfile tri.obj\n\tmaterial Shiny\n}\n"
+                    "light\n{\n\ttype Sphere\n\tposition 1 2 3\n\tradius 0.5\n\tnormal 0 2 0\n\temission 3 3 3\n}\n"
+                    "light\n{\n\ttype Quad\n\tposition 0 1 0\n\tv1 1 1 0\n\tv2 0 1 1\n\temission 4 4 4\n}\n")
+        sc = host.Scene.load(d, "q")
+        mi = sc.mesh_info(0)
+        dp = mi["disney"]
+        assert dp.color.tuple() == (0.25, 0.5, 0.75) and dp.metallic == 1.0 and dp.specularTint == pytest.approx(0.3)
+        assert dp.brdfType == S.GLASS and dp.roughness == 0.125
+        assert dp.specular == 0.5 and dp.sheenTint == 0.5 and dp.clearcoatGloss == 1.0 and dp.albedoID == 0  # defaults
+        l0, l1 = sc.light(0), sc.light(1)
+        assert l0.shape == S.SPHERE and l0.area == pytest.approx(4 * math.pi * 0.25) and l0.normal.tuple() == (0, 1, 0)
+        assert l1.shape == S.QUAD and l1.u.tuple() == (1, 0, 0) and l1.v.tuple() == (0, 0, 1)
+        assert l1.normal.tuple() == (0, -1, 0) and l1.area == pytest.approx(1.0) and l1.radius == 0.0
+        info = sc.info()
+        assert info.n_spheres == 1 and info.n_quads == 1 and info.n_lights == 2
+
+
+def test_scene_errors(host):
+    from minimaloptix_b200 import MoxError
+    with pytest.raises(MoxError):
+        host.Scene.load("/nonexistent", "nope")
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "e")
+        os.makedirs(d)
+        with open(os.path.join(d, "e.scene"), "w") as f:
+            f.write("mesh\n{\n\tfile a.obj\n\tmaterial Missing\n}\n")
+        with pytest.raises(MoxError, match="Could not find material"):
+            host.Scene.load(d, "e")
+
+
+def test_set_cam_params_closed_form(host):
+    c = host.set_cam_params((3, 3, 2), (0, 0, -1), (0, 1, 0), 20, 16 / 9, 0.5, math.sqrt(27))
+    assert c.origin.tuple() == (3, 3, 2) and c.lensRadius == 0.25
+    w = np.array([3, 3, 3]) / math.sqrt(27)
+    u = np.cross([0, 1, 0], w); u /= np.linalg.norm(u)
+    v = np.cross(w, u)
+    assert np.allclose(c.u.tuple(), u, atol=1e-6) and np.allclose(c.v.tuple(), v, atol=1e-6)
+    hh = math.tan(math.radians(20) / 2)
+    focus = math.sqrt(27)
+    assert np.allclose(c.vertical.tuple(), 2 * focus * hh * v, atol=1e-5)
+    assert np.allclose(c.horizontal.tuple(), 2 * focus * hh * 16 / 9 * u, atol=1e-5)
+    centre = np.array(c.scrLowerLeftCorner.tuple()) + 0.5 * np.array(c.horizontal.tuple()) + 0.5 * np.array(c.vertical.tuple())
+    assert np.allclose(centre, [0, 0, -1], atol=1e-5)  # the focal plane passes through lookAt
+    p = host.set_cam_params((0, 0, 5), (0, 0, 0), (0, 1, 0), 45, 1.0, 0.0, 1.0)
+    assert p.lensRadius == 0.0  # pinhole == aperture 0
+
+
+def test_set_quad_params(host):
+    q = host.set_quad_params((-5, 5, 5), (0, 0, -10), (10, 0, 0))
+    n = np.cross([10, 0, 0], [0, 0, -10]); n = n / np.linalg.norm(n)
+    assert np.allclose([q.plane.x, q.plane.y, q.plane.z], n)
+    assert q.plane.w == pytest.approx(np.dot(n, [-5, 5, 5]))
+    assert np.allclose(q.v1.tuple(), [0, 0, -0.1]) and np.allclose(q.v2.tuple(), [0.1, 0, 0])
+    assert q.anchor.tuple() == (-5, 5, 5)
+
+
+def test_quantisation_and_flip(host):
+    acc = np.zeros((2, 3, 3), dtype=np.float32)
+    acc[0, 0] = [0.5, 1.0, 2.0]      # bottom-left in accumulator space
+    acc[1, 2] = [4 * 0.5, 4 * 0.25, 0]
+    img = host.accum_to_rgb8(acc, 1)
+    assert img[1, 0].tolist() == [128, 255, 255]   # 0.5 -> 128, 1.0 -> 255, clamp; row flipped
+    img4 = host.accum_to_rgb8(acc, 4)
+    assert img4[0, 2].tolist() == [128, 64, 0]     # accu / N before quantisation (0.25 -> round(16383.75)=16384 >> 8 = 64)
+
+
+def test_png_and_accum_roundtrip(host):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, size=(37, 53, 3), dtype=np.uint8)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "x.png")
+        host.write_image(p, rgb)
+        assert np.array_equal(np.asarray(Image.open(p).convert("RGB")), rgb)
+        acc = rng.random((37, 53, 3)).astype(np.float32)
+        q = os.path.join(tmp, "x.moxa")
+        host.write_accum(q, acc, 17)
+        back, n = host.read_accum(q, 53, 37)
+        assert n == 17 and np.array_equal(back, acc)
+
+
+def test_builtin_scenes_are_deterministic(host):
+    a, b = host.Scene.builtin("random_spheres"), host.Scene.builtin("random_spheres")
+    ia, ib = a.info(), b.info()
+    assert ia.n_spheres == 259 and ia.n_quads == 33 and ia.n_items == 292
+    assert bytes(ia) == bytes(ib)
+    s = host.Scene.builtin("spheres_lens").info()
+    assert (s.n_spheres, s.n_quads, s.vfov, s.aperture) == (3, 2, 20.0, 0.5) and s.focus == pytest.approx(math.sqrt(27))
+    i1, i2 = host.Scene.builtin("interior", 50000), host.Scene.builtin("interior", 50000)
+    assert i1.info().n_triangles == i2.info().n_triangles and i1.mesh_hash(10) == i2.mesh_hash(10)
+    soup = host.Scene.builtin("soup", 1000, 3)
+    v, idx = soup.mesh_arrays(0)
+    assert v.shape == (3000, 3) and idx.shape == (1000, 3) and v.min() > -0.1 and v.max() < 1.1
+
+
+def test_launch_seed_schedule(host, orc):
+    assert host.launch_seed(0, 0xC0FFEE) == np.int32(np.uint32(orc.backend().tea16(0, 0xC0FFEE)))
+    assert len({host.launch_seed(i, 1) for i in range(64)}) == 64
