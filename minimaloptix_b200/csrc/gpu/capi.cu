@@ -69,6 +69,7 @@ struct mox_ctx {
 
   // device scene
   DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights;
+  DevBuf dQueryO, dQueryD, dQueryCounters;  // raw ray queries
   BvhNode2* dNodes = nullptr;
   float4* dPacked = nullptr;
   int nNodes = 0, nValid = 0;
@@ -270,7 +271,10 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     tm.begin(ST_EXTEND, c->stream);
     launchExtend(lc, lc.pb.qCur, count, depth);
     tm.end(c->stream);
-    c->extendLaunches++; c->kernelLaunches++;
+    tm.begin(ST_SHADE, c->stream);
+    launchLogic(lc, lc.pb.qCur, count, depth);
+    tm.end(c->stream);
+    c->extendLaunches++; c->kernelLaunches += 2;
     CUCK(c, cudaMemcpyAsync(host, pb.counters, 8 * 4, cudaMemcpyDeviceToHost, c->stream));
     CUCK(c, cudaStreamSynchronize(c->stream));
     uint32_t matCount[Q_COUNT];
@@ -282,7 +286,10 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     tm.end(c->stream);
     if (matCount[Q_DISNEY] && lc.scene.nLights) {
       tm.begin(ST_SHADOW, c->stream);
-      launchShadowAndApply(lc, matCount[Q_DISNEY]);
+      launchShadow(lc, matCount[Q_DISNEY]);
+      tm.end(c->stream);
+      tm.begin(ST_SHADE, c->stream);
+      launchApply(lc, matCount[Q_DISNEY]);
       tm.end(c->stream);
       c->kernelLaunches += 2;
     }
@@ -382,7 +389,8 @@ void mox_destroy(mox_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights}) b->release();
+  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dQueryO,
+                   &c->dQueryD, &c->dQueryCounters}) b->release();
   for (auto& b : c->otherOwned) b.release();
   cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dAccu); cudaFree(c->dOwned);
   freePaths(c->pb);
@@ -665,18 +673,25 @@ int mox_get_stats(mox_ctx* c, mox_stats* s) {
 int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* dev_hits, float* out_ms) {
   if (!c) return MOX_ERR_INVALID;
   if (n && (!dev_rays || !dev_hits)) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (n > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "too many rays");
   if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
+  if (out_ms) *out_ms = 0.f;
+  if (!n) return MOX_OK;
   int rc = bind(c);
   if (rc) return rc;
   bool count = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
-  uint32_t* counters = nullptr;
-  if (count) {
-    if ((rc = ensurePaths(c, std::max<size_t>(c->pb.capacity, 1), c->lights.size(), 1))) return rc;
-    counters = c->pb.counters;
-    CUCK(c, cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream));
-  }
+  if ((rc = ensure(c, c->dQueryO, n * 16))) return rc;
+  if ((rc = ensure(c, c->dQueryD, n * 16))) return rc;
+  if ((rc = ensure(c, c->dQueryCounters, C_WORDS * 4))) return rc;
+  uint32_t* counters = (uint32_t*)c->dQueryCounters.p;
+  CUCK(c, cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream));
+  launchSplitRays((const float4*)dev_rays, (float4*)c->dQueryO.p, (float4*)c->dQueryD.p, n, c->stream);
+  TraceJob job;
+  job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n;
+  job.cursor = counters + C_CURSOR; job.hits = (float4*)dev_hits; job.shC = nullptr; job.counters = counters;
+  CUCK(c, cudaMemsetAsync(job.cursor, 0, 4, c->stream));
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
-  launchTraceClosest(sceneView(c), (const float4*)dev_rays, n, (float4*)dev_hits, count, counters, c->stream);
+  launchTraverse(sceneView(c), job, false, count, c->stream);
   CUCK(c, cudaEventRecord(c->ev1, c->stream));
   CUCK(c, cudaEventSynchronize(c->ev1));
   CUCK(c, cudaGetLastError());
@@ -715,18 +730,33 @@ int mox_trace_closest(mox_ctx* c, const float* rays, size_t n, void* hits) {
 int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
   if (!c) return MOX_ERR_INVALID;
   if (n && (!rays || !out_rgb)) return fail(c, MOX_ERR_INVALID, "null argument");
+  if (n > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "too many rays");
   if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
   if (!n) return MOX_OK;
   int rc = bind(c);
   if (rc) return rc;
-  void *dRays = nullptr, *dOut = nullptr;
+  void *dRays = nullptr, *dOut = nullptr, *dC = nullptr;
   CUCK(c, cudaMalloc(&dRays, n * 32));
   CUCK(c, cudaMalloc(&dOut, n * 12));
-  CUCK(c, cudaMemcpy(dRays, rays, n * 32, cudaMemcpyHostToDevice));
-  launchTraceShadow(sceneView(c), (const float4*)dRays, n, (float*)dOut, c->stream);
+  CUCK(c, cudaMalloc(&dC, n * 16));
+  if ((rc = ensure(c, c->dQueryO, n * 16)) || (rc = ensure(c, c->dQueryD, n * 16)) || (rc = ensure(c, c->dQueryCounters, C_WORDS * 4))) {
+    cudaFree(dRays); cudaFree(dOut); cudaFree(dC);
+    return rc;
+  }
+  uint32_t* counters = (uint32_t*)c->dQueryCounters.p;
+  cudaMemcpy(dRays, rays, n * 32, cudaMemcpyHostToDevice);
+  cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream);
+  launchSplitRays((const float4*)dRays, (float4*)c->dQueryO.p, (float4*)c->dQueryD.p, n, c->stream);
+  launchFillOnes((float4*)dC, n, c->stream);
+  TraceJob job;
+  job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n;
+  job.cursor = counters + C_CURSOR; job.hits = nullptr; job.shC = (float4*)dC; job.counters = counters;
+  launchTraverse(sceneView(c), job, true, false, c->stream);
+  launchCopyRgb((const float4*)dC, (float*)dOut, n, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out_rgb, dOut, n * 12, cudaMemcpyDeviceToHost);
-  cudaFree(dRays); cudaFree(dOut);
+  cudaFree(dRays); cudaFree(dOut); cudaFree(dC);
   if (e != cudaSuccess) return fail(c, MOX_ERR_CUDA, cudaGetErrorString(e));
   return MOX_OK;
 }

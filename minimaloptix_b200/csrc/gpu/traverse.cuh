@@ -8,6 +8,7 @@
 // 1e-5 relative) and may use any rounding.
 #pragma once
 #include "gpu_types.h"
+#include "traverse_job.h"
 #include "vec.cuh"
 
 struct Hit { float t; int prim; float beta, gamma; };
@@ -74,129 +75,146 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
 }
 
 #define MOX_STACK 64
+#define MOX_DONE ((int)0x80000000)   // sentinel "no more nodes" (same bit pattern as an empty child)
+#define MOX_FETCH_THRESHOLD 20       // refill a warp's idle lanes when fewer than this many are traversing
 
-// Closest hit over the binary BVH.  COUNT adds node-visit / primitive-test counters.
-template <bool COUNT>
-MOX_D Hit traceClosest(const SceneView& s, const float3& o, const float3& d, float tmin, float tmax, uint32_t* nodeVisits,
-                       uint32_t* primTests) {
-  Hit best; best.t = tmax; best.prim = -1; best.beta = 0.f; best.gamma = 0.f;
-  RayPre r = prepRay(o, d, tmin);
+// Persistent-thread while-while traversal (Aila & Laine 2009) over the binary BVH.
+//   * warps fetch rays from a global cursor: 32 at start, then whenever fewer than
+//     MOX_FETCH_THRESHOLD lanes are still traversing the idle lanes are refilled;
+//   * inner loop descends inner nodes until the lane reaches a leaf, then the leaf's
+//     primitives are tested (closest hit: (t, id) lexicographic; any hit: Disney prims only,
+//     NORMAL blocks, GLASS tints — SURVEY.md §8 a-11, Material.cu:225-232);
+//   * per-lane traversal stack in local memory (far children only).
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const TraceJob& job) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned ltMask = (1u << lane) - 1u;
+  const float INF = __int_as_float(0x7f800000);
   int stack[MOX_STACK];
-  int sp = 0;
-  int cur = 0;  // root
+  int sp = 0, cur = MOX_DONE;
+  bool active = false, exhausted = false;
+  uint32_t rayId = 0;
+  RayPre r;
+  r.o = r.d = r.idir = mk3(0.f); r.tmin = 0.f;
+  float tBest = 0.f, bBeta = 0.f, bGamma = 0.f;
+  int bPrim = -1;
+  float3 atten = mk3(1.f);
   uint32_t nv = 0, np = 0;
+
   while (true) {
-    if (cur >= 0) {
-      const BvhNode2* nd = s.nodes + cur;
-      float4 a = __ldg(&nd->c0xy), b = __ldg(&nd->c1xy), z = __ldg(&nd->cz);
-      int4 ref = __ldg(&nd->ref);
-      if (COUNT) nv++;
-      float t0 = ref.x == MOX_EMPTY_CHILD ? __int_as_float(0x7f800000) : boxEntry(r, a.x, a.y, a.z, a.w, z.x, z.y, best.t);
-      float t1 = ref.y == MOX_EMPTY_CHILD ? __int_as_float(0x7f800000) : boxEntry(r, b.x, b.y, b.z, b.w, z.z, z.w, best.t);
-      bool h0 = t0 < __int_as_float(0x7f800000), h1 = t1 < __int_as_float(0x7f800000);
-      if (h0 && h1) {
-        bool swap = t1 < t0;
-        int nearC = swap ? ref.y : ref.x, farC = swap ? ref.x : ref.y;
-        if (sp < MOX_STACK) stack[sp++] = farC;
-        cur = nearC;
-        continue;
-      } else if (h0 || h1) {
-        cur = h0 ? ref.x : ref.y;
-        continue;
-      }
-    } else {
-      uint32_t leaf = (uint32_t)~cur;
-      uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
-      for (uint32_t k = 0; k < count; ++k) {
-        const float4* rec = s.packed + (size_t)(first + k) * MOX_PACKED_F4;
-        float4 r0 = __ldg(rec);
-        if (COUNT) np++;
-        uint32_t idbits = __float_as_uint(r0.w);
-        uint32_t type = idbits >> 30;
-        int id = (int)(idbits & 0x3fffffffu);
-        if (type == PT_TRI) {
-          float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-          float t, be, ga;
-          if (triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < best.t || (t == best.t && id < best.prim))) {
-            best.t = t; best.prim = id; best.beta = be; best.gamma = ga;
-          }
-        } else {
-          const Analytic* an = s.analytic + __float_as_int(r0.x);
-          if (type == PT_SPHERE) {
-            float t;
-            if (sphereTest(__ldg(&an->a), o, d, tmin, best.t, id < best.prim, t)) { best.t = t; best.prim = id; best.beta = 0.f; best.gamma = 0.f; }
-          } else {
-            Analytic q;
-            q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
-            float t, a1, a2;
-            if (quadTest(q, o, d, tmin, t, a1, a2) && (t < best.t || (t == best.t && id < best.prim))) {
-              best.t = t; best.prim = id; best.beta = a1; best.gamma = a2;
+    // ---------------- refill idle lanes
+    if (!exhausted) {
+      unsigned idle = __ballot_sync(FULL, !active);
+      if (idle) {
+        const int leader = __ffs(idle) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(job.cursor, (uint32_t)__popc(idle));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          uint32_t i = base + __popc(idle & ltMask);
+          if (i < job.count) {
+            rayId = job.queue ? __ldg(job.queue + i) : i;
+            float4 ro = __ldg(job.rayO + rayId), rd = __ldg(job.rayD + rayId);
+            if (!(ANYHIT && rd.w < 0.f)) {
+              r = prepRay(mk3(ro), mk3(rd), ro.w);
+              tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
+              atten = mk3(1.f);
+              sp = 0; cur = 0;  // root
+              active = true;
+              if (COUNT) { nv = 0; np = 0; }
             }
           }
         }
+        if (base + __popc(idle) >= job.count) exhausted = true;
       }
     }
-    if (sp == 0) break;
-    cur = stack[--sp];
-  }
-  if (COUNT) { *nodeVisits = nv; *primTests = np; }
-  return best;
-}
-
-// Shadow-ray transmittance with the order-independent rule (reference
-// any-hit Material.cu:225-232): only Disney primitives occlude; any NORMAL hit in
-// (tmin, tmax) -> 0, otherwise the product of the GLASS colours.
-MOX_D float3 traceShadow(const SceneView& s, const float3& o, const float3& d, float tmin, float tmax) {
-  float3 atten = mk3(1.f);
-  RayPre r = prepRay(o, d, tmin);
-  int stack[MOX_STACK];
-  int sp = 0;
-  int cur = 0;
-  while (true) {
-    if (cur >= 0) {
-      const BvhNode2* nd = s.nodes + cur;
-      float4 a = __ldg(&nd->c0xy), b = __ldg(&nd->c1xy), z = __ldg(&nd->cz);
-      int4 ref = __ldg(&nd->ref);
-      bool h0 = ref.x != MOX_EMPTY_CHILD && boxEntry(r, a.x, a.y, a.z, a.w, z.x, z.y, tmax) < __int_as_float(0x7f800000);
-      bool h1 = ref.y != MOX_EMPTY_CHILD && boxEntry(r, b.x, b.y, b.z, b.w, z.z, z.w, tmax) < __int_as_float(0x7f800000);
-      if (h0 && h1) { if (sp < MOX_STACK) stack[sp++] = ref.y; cur = ref.x; continue; }
-      else if (h0 || h1) { cur = h0 ? ref.x : ref.y; continue; }
-    } else {
-      uint32_t leaf = (uint32_t)~cur;
-      uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
-      for (uint32_t k = 0; k < count; ++k) {
-        const float4* rec = s.packed + (size_t)(first + k) * MOX_PACKED_F4;
-        float4 r0 = __ldg(rec);
-        uint32_t idbits = __float_as_uint(r0.w);
-        uint32_t type = idbits >> 30;
-        uint32_t id = idbits & 0x3fffffffu;
-        const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
-        if (__ldg(&m->kind) != MOX_MAT_DISNEY) continue;
-        bool hit;
-        if (type == PT_TRI) {
-          float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-          float t, be, ga;
-          hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && t < tmax;
+    if (!__any_sync(FULL, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---------------- traverse until too few lanes are busy.  Every lane runs the same
+    // skeleton (idle lanes hold cur == MOX_DONE) so the two __syncwarp()s are legal; they force
+    // the warp to reconverge between the inner-node loop and the leaf tests — without them the
+    // lanes drift through the leaf code one by one (measured: 1.5 threads per instruction).
+    while (true) {
+      while (cur >= 0) {  // inner nodes
+        const BvhNode2* nd = s.nodes + cur;
+        float4 a = __ldg(&nd->c0xy), b = __ldg(&nd->c1xy), z = __ldg(&nd->cz);
+        int4 ref = __ldg(&nd->ref);
+        if (COUNT) nv++;
+        float t0 = ref.x == MOX_EMPTY_CHILD ? INF : boxEntry(r, a.x, a.y, a.z, a.w, z.x, z.y, tBest);
+        float t1 = ref.y == MOX_EMPTY_CHILD ? INF : boxEntry(r, b.x, b.y, b.z, b.w, z.z, z.w, tBest);
+        bool h0 = t0 < INF, h1 = t1 < INF;
+        if (h0 && h1) {
+          bool swp = t1 < t0;
+          if (sp < MOX_STACK) stack[sp++] = swp ? ref.x : ref.y;
+          cur = swp ? ref.y : ref.x;
+        } else if (h0 || h1) {
+          cur = h0 ? ref.x : ref.y;
         } else {
-          const Analytic* an = s.analytic + __float_as_int(r0.x);
-          if (type == PT_SPHERE) {
-            float t;
-            hit = sphereTest(__ldg(&an->a), o, d, tmin, tmax, false, t);
+          cur = sp ? stack[--sp] : MOX_DONE;
+        }
+      }
+      __syncwarp();
+      if (cur != MOX_DONE) {  // leaf
+        uint32_t leaf = (uint32_t)~cur;
+        uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
+        bool blocked = false;
+        for (uint32_t k = 0; k < count; ++k) {
+          const float4* rec = s.packed + (size_t)(first + k) * MOX_PACKED_F4;
+          float4 r0 = __ldg(rec);
+          if (COUNT) np++;
+          uint32_t idbits = __float_as_uint(r0.w);
+          uint32_t type = idbits >> 30;
+          int id = (int)(idbits & 0x3fffffffu);
+          float t = 0.f, be = 0.f, ga = 0.f;
+          bool hit;
+          if (type == PT_TRI) {
+            float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+            hit = triTest(r.o, r.d, r.tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
           } else {
-            Analytic q;
-            q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
-            float t, a1, a2;
-            hit = quadTest(q, o, d, tmin, t, a1, a2) && t < tmax;
+            const Analytic* an = s.analytic + __float_as_int(r0.x);
+            if (type == PT_SPHERE) {
+              hit = sphereTest(__ldg(&an->a), r.o, r.d, r.tmin, tBest, !ANYHIT && id < bPrim, t);
+            } else {
+              Analytic q;
+              q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
+              hit = quadTest(q, r.o, r.d, r.tmin, t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+            }
+          }
+          if (hit) {
+            if (ANYHIT) {
+              // geometry first, material only on a hit: non-Disney prims do not occlude shadow rays
+              const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
+              if (__ldg(&m->kind) == MOX_MAT_DISNEY) {
+                if (__ldg((const int*)&m->dis.brdfType) == GLASS) atten *= mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
+                else { blocked = true; break; }
+              }
+            } else {
+              tBest = t; bPrim = id; bBeta = be; bGamma = ga;
+            }
           }
         }
-        if (hit) {
-          if (m->dis.brdfType == GLASS) atten *= f3(m->dis.color);
-          else return mk3(0.f);
-        }
+        cur = (blocked || sp == 0) ? MOX_DONE : stack[--sp];
+        if (ANYHIT && blocked) atten = mk3(0.f);
       }
+      __syncwarp();
+      if (active && cur == MOX_DONE) {  // ray finished
+        if (ANYHIT) {
+          float4 c = job.shC[rayId];
+          job.shC[rayId] = make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w);
+        } else {
+          job.hits[rayId] = make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma);
+        }
+        if (COUNT) {
+          atomicAdd((unsigned long long*)(job.counters + 10), (unsigned long long)nv);
+          atomicAdd((unsigned long long*)(job.counters + 12), (unsigned long long)np);
+        }
+        active = false;
+      }
+      unsigned busy = __ballot_sync(FULL, active);
+      if (busy == 0u || (!exhausted && __popc(busy) < MOX_FETCH_THRESHOLD)) break;
     }
-    if (sp == 0) break;
-    cur = stack[--sp];
   }
-  return atten;
 }

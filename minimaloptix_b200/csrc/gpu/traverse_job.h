@@ -1,0 +1,22 @@
+// traverse_job.h — launch descriptor of the persistent traversal kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// One batch of rays for the persistent traversal kernel.
+//   rayO[id] = (origin, tmin)   rayD[id] = (direction, tmax); tmax < 0 marks an unused slot
+//   queue    : optional indirection, ray id = queue[i] for i < count
+//   cursor   : global fetch cursor, zeroed before the launch
+//   hits     : closest hit: hits[id] = (t, prim id as int bits or -1, beta, gamma)
+//   shC      : any hit: shC[id].xyz *= transmittance
+struct TraceJob {
+  const float4* rayO;
+  const float4* rayD;
+  const uint32_t* queue;
+  uint32_t count;
+  uint32_t* cursor;
+  float4* hits;
+  float4* shC;
+  uint32_t* counters;
+};
+

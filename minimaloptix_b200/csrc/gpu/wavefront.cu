@@ -3,11 +3,12 @@
 // is a path in a wavefront, advanced one bounce per iteration:
 //
 //   k_generate   camera()                      Camera.cu:21-36
-//   k_extend     rtTrace closest hit + miss (miss.cu:10-12) + light() (Material.cu:238-240)
-//                + the depth test every scattering program starts with (Material.cu:29,50,73,119);
-//                surviving paths are binned into per-material queues
+//   k_traverse   rtTrace: persistent-thread traversal, closest hit (extend rays) or shadow
+//                transmittance (disneyAnyHit, Material.cu:225-232) — traverse.cuh
+//   k_logic      miss (miss.cu:10-12), light() (Material.cu:238-240) and the depth test every
+//                scattering program starts with (Material.cu:29,50,73,119); surviving paths are
+//                binned into per-material queues
 //   k_shade_*    lambertian / metal / glass / disney   Material.cu:28-223, disney.h
-//   k_shadow     shadow rtTrace + disneyAnyHit         Material.cu:189-203, 225-232
 //   k_apply      adds the NEE terms to the path radiance in light order (deterministic)
 //   k_accumulate clamp + accuBuffer +=                 Camera.cu:39-41
 //
@@ -73,28 +74,31 @@ __global__ void __launch_bounds__(TPB) k_generate(LaunchCtx c, uint32_t nPaths) 
   c.pb.qCur[p] = p;
 }
 
-// ------------------------------------------------------------------ extend + classify
-template <bool COUNT>
-__global__ void __launch_bounds__(TPB) k_extend(LaunchCtx c, const uint32_t* __restrict__ queue, uint32_t count, uint32_t depth) {
+// ------------------------------------------------------------------ traversal + classify
+constexpr int TRAV_TPB = 128;
+
+template <bool ANYHIT, bool COUNT>
+__global__ void __launch_bounds__(TRAV_TPB) k_traverse(SceneView s, TraceJob job) {
+  traverseWarpPersistent<ANYHIT, COUNT>(s, job);
+}
+
+// Consumes the closest-hit records of the current queue: miss (miss.cu:10-12), light
+// (Material.cu:238-240) and the depth test every scattering program starts with
+// (Material.cu:29,50,73,119) terminate the path here; the rest is binned by material.
+__global__ void __launch_bounds__(TPB) k_logic(LaunchCtx c, const uint32_t* __restrict__ queue, uint32_t count, uint32_t depth) {
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
   uint32_t path = queue[i];
-  float4 ro = c.pb.rayO[path], rd = c.pb.rayD[path];
-  uint32_t nv = 0, np = 0;
-  Hit h = traceClosest<COUNT>(c.scene, mk3(ro), mk3(rd), ro.w, rd.w, &nv, &np);
-  if (COUNT) {
-    // 64-bit totals kept as two words; one atomic per warp would be nicer, this is the counting build only
-    atomicAdd((unsigned long long*)(c.pb.counters + C_NODEVIS_LO), (unsigned long long)nv);
-    atomicAdd((unsigned long long*)(c.pb.counters + C_PRIMTEST_LO), (unsigned long long)np);
-  }
+  float4 h = c.pb.hit[path];
+  int prim = __float_as_int(h.y);
   const RenderParams& rp = c.rp;
-  if (h.prim < 0) {  // miss: payload colour (1,1,1) * bgColor
+  if (prim < 0) {  // miss: payload colour (1,1,1) * bgColor
     float4 T = c.pb.thr[path], R = c.pb.rad[path];
     float3 r = mk3(R) + mk3(T) * (mk3(1.f) * rp.bg);
     c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
     return;
   }
-  PrimDesc pd = c.scene.prims[h.prim];
+  PrimDesc pd = c.scene.prims[prim];
   const GpuMaterial* m = c.scene.mats + (pd.typeMat >> 2);
   int kind = __ldg(&m->kind);
   if (kind == MOX_MAT_LIGHT) {
@@ -110,7 +114,6 @@ __global__ void __launch_bounds__(TPB) k_extend(LaunchCtx c, const uint32_t* __r
     c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
     return;
   }
-  c.pb.hit[path] = make_float4(h.t, __int_as_float(h.prim), h.beta, h.gamma);
   int q = kind == MOX_MAT_LAMBERTIAN ? Q_LAMBERT
         : kind == MOX_MAT_METAL ? Q_METAL
         : kind == MOX_MAT_GLASS ? Q_DIELECTRIC
@@ -280,11 +283,9 @@ __global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t coun
     L = pointOnLight - a.front;
     float lightDst = length(L);
     L = normalize(L);
-    size_t slot = (size_t)i * nL + li;
+    size_t slot = (size_t)li * count + i;  // light-major: neighbouring lanes aim at the same light
     float3 contrib = mk3(0.f);
-    float active = 0.f;
     if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
-      active = 1.f;
       shadowCount++;
       H = normalize(L + V);
       float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
@@ -295,8 +296,10 @@ __global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t coun
       }
     }
     float3 pc = Tprev * contrib;
-    c.pb.shO[slot] = make_float4(a.front.x, a.front.y, a.front.z, lightDst - c.rp.eps);
-    c.pb.shD[slot] = make_float4(L.x, L.y, L.z, active);
+    // a zero contribution needs no shadow ray (it is still counted, as the reference traces it)
+    bool trace = pc.x != 0.f || pc.y != 0.f || pc.z != 0.f;
+    c.pb.shO[slot] = make_float4(a.front.x, a.front.y, a.front.z, c.rp.eps);
+    c.pb.shD[slot] = make_float4(L.x, L.y, L.z, trace ? lightDst - c.rp.eps : -1.f);
     c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
   }
   if (shadowCount) atomicAdd(c.pb.counters + C_SHADOW, shadowCount);
@@ -317,26 +320,13 @@ __global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t coun
   }
 }
 
-__global__ void __launch_bounds__(TPB) k_shadow(LaunchCtx c, uint32_t nSlots) {
-  uint32_t i = blockIdx.x * TPB + threadIdx.x;
-  if (i >= nSlots) return;
-  float4 d = c.pb.shD[i];
-  if (d.w == 0.f) return;
-  float4 o = c.pb.shO[i];
-  float4 col = c.pb.shC[i];
-  if (col.x == 0.f && col.y == 0.f && col.z == 0.f) return;
-  float3 atten = traceShadow(c.scene, mk3(o), mk3(d), c.rp.eps, o.w);
-  float3 r = mk3(col) * atten;
-  c.pb.shC[i] = make_float4(r.x, r.y, r.z, 0.f);
-}
-
 __global__ void __launch_bounds__(TPB) k_apply(LaunchCtx c, uint32_t count) {
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
   uint32_t path = c.pb.qMat[Q_DISNEY][i];
   const int nL = c.scene.nLights;
   float3 direct = mk3(0.f);
-  for (int li = 0; li < nL; ++li) direct += mk3(c.pb.shC[(size_t)i * nL + li]);
+  for (int li = 0; li < nL; ++li) direct += mk3(c.pb.shC[(size_t)li * count + i]);
   float3 r = mk3(c.pb.rad[path]) + direct;
   c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
 }
@@ -362,27 +352,19 @@ __global__ void __launch_bounds__(TPB) k_accumulate(LaunchCtx c, uint32_t nSampl
 }
 
 // ------------------------------------------------------------------ raw ray queries
-template <bool COUNT>
-__global__ void __launch_bounds__(TPB) k_trace_closest(SceneView s, const float4* __restrict__ rays, size_t n,
-                                                        float4* __restrict__ hits, uint32_t* counters) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  float4 ro = rays[2 * i], rd = rays[2 * i + 1];
-  uint32_t nv = 0, np = 0;
-  Hit h = traceClosest<COUNT>(s, mk3(ro), mk3(rd), ro.w, rd.w, &nv, &np);
-  hits[i] = make_float4(h.t, __int_as_float(h.prim), h.beta, h.gamma);
-  if (COUNT) {
-    atomicAdd((unsigned long long*)(counters + C_NODEVIS_LO), (unsigned long long)nv);
-    atomicAdd((unsigned long long*)(counters + C_PRIMTEST_LO), (unsigned long long)np);
-  }
+// out[i] = transmittance (the shC buffer is pre-set to 1)
+__global__ void k_fill_ones(float4* __restrict__ p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = make_float4(1.f, 1.f, 1.f, 0.f);
 }
-
-__global__ void __launch_bounds__(TPB) k_trace_shadow(SceneView s, const float4* __restrict__ rays, size_t n, float* __restrict__ out) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  float4 ro = rays[2 * i], rd = rays[2 * i + 1];
-  float3 a = traceShadow(s, mk3(ro), mk3(rd), ro.w, rd.w);
-  out[3 * i] = a.x; out[3 * i + 1] = a.y; out[3 * i + 2] = a.z;
+__global__ void k_copy_rgb(const float4* __restrict__ src, float* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float4 v = src[i]; dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z; }
+}
+// split interleaved (o,tmin,d,tmax) rays into the two arrays the traversal kernel reads
+__global__ void k_split_rays(const float4* __restrict__ rays, float4* __restrict__ o, float4* __restrict__ d, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { o[i] = rays[2 * i]; d[i] = rays[2 * i + 1]; }
 }
 
 __global__ void k_pack_owned(const float* __restrict__ accu, const uint32_t* __restrict__ ownedPix, uint32_t nOwned, float* __restrict__ dst) {
@@ -410,10 +392,42 @@ void launchGenerate(const LaunchCtx& c, uint32_t nSamples) {
   uint32_t n = nSamples * c.nOwned;
   if (n) k_generate<<<grid(n), TPB, 0, c.stream>>>(c, n);
 }
+template <bool ANYHIT, bool COUNT>
+static unsigned persistentGrid(uint32_t count) {
+  static int blocksPerSm = 0, numSms = 0;
+  if (!blocksPerSm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, k_traverse<ANYHIT, COUNT>, TRAV_TPB, 0);
+    if (blocksPerSm < 1) blocksPerSm = 1;
+  }
+  unsigned full = (unsigned)(numSms * blocksPerSm);
+  unsigned need = (count + TRAV_TPB - 1) / TRAV_TPB;
+  return need < full ? need : full;
+}
+
+void launchTraverse(const SceneView& s, const TraceJob& job, bool anyHit, bool count, cudaStream_t stream) {
+  if (!job.count) return;
+  cudaMemsetAsync(job.cursor, 0, 4, stream);
+  if (anyHit) {
+    k_traverse<true, false><<<persistentGrid<true, false>(job.count), TRAV_TPB, 0, stream>>>(s, job);
+  } else if (count) {
+    k_traverse<false, true><<<persistentGrid<false, true>(job.count), TRAV_TPB, 0, stream>>>(s, job);
+  } else {
+    k_traverse<false, false><<<persistentGrid<false, false>(job.count), TRAV_TPB, 0, stream>>>(s, job);
+  }
+}
+
 void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
   if (!count) return;
-  if (c.countTraversal) k_extend<true><<<grid(count), TPB, 0, c.stream>>>(c, queue, count, depth);
-  else k_extend<false><<<grid(count), TPB, 0, c.stream>>>(c, queue, count, depth);
+  TraceJob job;
+  job.rayO = c.pb.rayO; job.rayD = c.pb.rayD; job.queue = queue; job.count = count;
+  job.cursor = c.pb.counters + C_CURSOR; job.hits = c.pb.hit; job.shC = nullptr; job.counters = c.pb.counters;
+  launchTraverse(c.scene, job, false, c.countTraversal, c.stream);
+}
+void launchLogic(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
+  if (count) k_logic<<<grid(count), TPB, 0, c.stream>>>(c, queue, count, depth);
 }
 void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
   if (!count) return;
@@ -424,23 +438,28 @@ void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
     case Q_DISNEY: k_shade_disney<<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
   }
 }
-void launchShadowAndApply(const LaunchCtx& c, uint32_t disneyCount) {
+void launchShadow(const LaunchCtx& c, uint32_t disneyCount) {
   if (!disneyCount || c.scene.nLights == 0) return;
   size_t slots = (size_t)disneyCount * c.scene.nLights;
-  k_shadow<<<grid(slots), TPB, 0, c.stream>>>(c, (uint32_t)slots);
-  k_apply<<<grid(disneyCount), TPB, 0, c.stream>>>(c, disneyCount);
+  TraceJob job;
+  job.rayO = c.pb.shO; job.rayD = c.pb.shD; job.queue = nullptr; job.count = (uint32_t)slots;
+  job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
+  launchTraverse(c.scene, job, true, false, c.stream);
+}
+void launchApply(const LaunchCtx& c, uint32_t disneyCount) {
+  if (disneyCount && c.scene.nLights) k_apply<<<grid(disneyCount), TPB, 0, c.stream>>>(c, disneyCount);
 }
 void launchAccumulate(const LaunchCtx& c, uint32_t nSamples) {
   if (c.nOwned) k_accumulate<<<grid(c.nOwned), TPB, 0, c.stream>>>(c, nSamples);
 }
-void launchTraceClosest(const SceneView& s, const float4* rays, size_t n, float4* hits, bool count, uint32_t* counters,
-                        cudaStream_t stream) {
-  if (!n) return;
-  if (count) k_trace_closest<true><<<grid(n), TPB, 0, stream>>>(s, rays, n, hits, counters);
-  else k_trace_closest<false><<<grid(n), TPB, 0, stream>>>(s, rays, n, hits, counters);
+void launchSplitRays(const float4* rays, float4* o, float4* d, size_t n, cudaStream_t stream) {
+  if (n) k_split_rays<<<grid(n), TPB, 0, stream>>>(rays, o, d, n);
 }
-void launchTraceShadow(const SceneView& s, const float4* rays, size_t n, float* out, cudaStream_t stream) {
-  if (n) k_trace_shadow<<<grid(n), TPB, 0, stream>>>(s, rays, n, out);
+void launchFillOnes(float4* p, size_t n, cudaStream_t stream) {
+  if (n) k_fill_ones<<<grid(n), TPB, 0, stream>>>(p, n);
+}
+void launchCopyRgb(const float4* src, float* dst, size_t n, cudaStream_t stream) {
+  if (n) k_copy_rgb<<<grid(n), TPB, 0, stream>>>(src, dst, n);
 }
 void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream) {
   if (nOwned) k_pack_owned<<<grid(nOwned), TPB, 0, stream>>>(accu, ownedPix, nOwned, dst);

@@ -4,13 +4,14 @@
 #include <stdint.h>
 #include <string>
 #include "gpu_types.h"
+#include "traverse_job.h"
 
 // Material queues built by the extend kernel.
 enum ShadeQueue { Q_LAMBERT = 0, Q_METAL = 1, Q_DIELECTRIC = 2, Q_DISNEY = 3, Q_COUNT = 4 };
 
 // Device counters (uint32 words).
 enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
-                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_WORDS = 16 };
+                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_WORDS = 16 };
 
 struct PathBuffers {
   size_t capacity = 0;      // paths
@@ -39,10 +40,14 @@ struct LaunchCtx {
 void launchGenerate(const LaunchCtx& c, uint32_t nSamples);
 void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth);
 void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth);
-void launchShadowAndApply(const LaunchCtx& c, uint32_t disneyCount);
+void launchLogic(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth);
+void launchShadow(const LaunchCtx& c, uint32_t disneyCount);
+void launchApply(const LaunchCtx& c, uint32_t disneyCount);
 void launchAccumulate(const LaunchCtx& c, uint32_t nSamples);
-void launchTraceClosest(const SceneView& s, const float4* rays, size_t n, float4* hits, bool count, uint32_t* counters,
-                        cudaStream_t stream);
-void launchTraceShadow(const SceneView& s, const float4* rays, size_t n, float* out, cudaStream_t stream);
+// Persistent traversal over one batch of rays (closest hit or shadow transmittance).
+void launchTraverse(const SceneView& s, const TraceJob& job, bool anyHit, bool count, cudaStream_t stream);
+void launchSplitRays(const float4* rays, float4* o, float4* d, size_t n, cudaStream_t stream);
+void launchFillOnes(float4* p, size_t n, cudaStream_t stream);
+void launchCopyRgb(const float4* src, float* dst, size_t n, cudaStream_t stream);
 void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream);
 void launchUnpackOwned(float* accu, const uint32_t* ownedPix, uint32_t nOwned, const float* src, cudaStream_t stream);
