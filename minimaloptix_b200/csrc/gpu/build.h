@@ -12,13 +12,32 @@ struct BuildInput {
   const float* verts = nullptr;        // device
   const Analytic* analytic = nullptr;  // device
   cudaEvent_t evStart = nullptr, evStop = nullptr;  // recorded around the build kernels when set
+  bool usePloc = true;   // false: Karras radix tree (fastest build, lower quality)
+  int plocRadius = 16;
 };
+
+// Scratch of the PLOC hierarchy builder (ploc.cu), allocated before the timed build.
+struct PlocScratch {
+  uint32_t* cid[2] = {nullptr, nullptr};
+  float4 *cLo[2] = {nullptr, nullptr}, *cHi[2] = {nullptr, nullptr};
+  uint32_t* nn = nullptr;
+  float4 *nodeLo = nullptr, *nodeHi = nullptr;
+  uint2* children = nullptr;
+  uint32_t *parent = nullptr, *size = nullptr, *leafPos = nullptr, *orderedIds = nullptr;
+  unsigned long long* tileSums = nullptr;
+  unsigned long long* hostTotal = nullptr;  // pinned
+};
+bool plocAlloc(PlocScratch& s, int n, std::string& err);
+void plocFree(PlocScratch& s);
+bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* primLo, const float4* primHi, int radius,
+               BvhNode2* outNodes, float rootLo[3], float rootHi[3], cudaStream_t stream, std::string& err);
 
 struct BuildOutput {
   BvhNode2* nodes = nullptr;  // device, owned by the caller after a successful build
   int nNodes = 0;
   float4* packed = nullptr;   // device, 3 float4 per valid primitive in leaf order
   int nValid = 0, nInvalid = 0;
+  int iterations = 0;
   float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0};
   float4 *scratchLo = nullptr, *scratchHi = nullptr;  // builder-internal
 };

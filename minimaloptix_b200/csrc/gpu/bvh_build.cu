@@ -394,7 +394,9 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   const int nInnerMax = std::max(n - 1, 1);
   // small: [0..5] centroid bounds, [6] invalid count, [7] error flag, [8..11] tile counters, [16..16+1024) histograms
   const size_t smallWords = 16 + 1024;
+  PlocScratch ploc;
   auto freeScratch = [&]() {
+    plocFree(ploc);
     cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(small); cudaFree(status);
     cudaFree(boxLo); cudaFree(boxHi); cudaFree(children); cudaFree(range); cudaFree(parentInternal);
     cudaFree(parentLeaf); cudaFree(nodeLo); cudaFree(nodeHi); cudaFree(arrivals);
@@ -415,6 +417,10 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   CKB(cudaMalloc(&out.nodes, (size_t)nInnerMax * sizeof(BvhNode2)));
   CKB(cudaMalloc(&out.packed, (size_t)n * 48));
   out.scratchLo = boxLo; out.scratchHi = boxHi;
+  if (in.usePloc && n >= 2) {
+    std::string perr;
+    if (!plocAlloc(ploc, n, perr)) return bail(perr);
+  }
   if (in.evStart) CKB(cudaEventRecord(in.evStart, stream));
 
   uint32_t init[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -443,7 +449,8 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out.nValid = nValid;
   out.nInvalid = (int)hostSmall[6];
 
-  if (nValid > 0) k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, out.packed);
+  if (nValid > 0 && (nValid <= 1 || !in.usePloc))
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, out.packed);
   if (nValid <= 1) {
     BvhNode2 root;
     root.c0xy = root.c1xy = root.cz = make_float4(0, 0, 0, 0);
@@ -470,6 +477,16 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
 
   const int nInner = nValid - 1;
   out.nNodes = nInner;
+  if (in.usePloc) {
+    std::string perr;
+    if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, stream, perr)) return bail(perr);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, out.packed);
+    if (in.evStop) CKB(cudaEventRecord(in.evStop, stream));
+    CKB(cudaStreamSynchronize(stream));
+    CKB(cudaGetLastError());
+    freeScratch();
+    return true;
+  }
   k_karras<<<divUp(nInner, B), B, 0, stream>>>(nValid, kin, children, range, parentInternal, parentLeaf);
   k_refit<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, boxLo, boxHi, children, parentInternal, parentLeaf, nodeLo, nodeHi, arrivals);
   k_emit2<<<divUp(nInner, B), B, 0, stream>>>(nValid, vin, boxLo, boxHi, children, range, nodeLo, nodeHi, out.nodes);

@@ -562,6 +562,9 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   in.verts = (const float*)c->dVerts.p;
   in.analytic = (const Analytic*)c->dAnalytic.p;
   in.evStart = c->ev0; in.evStop = c->ev1;
+  in.usePloc = (flags & MOX_ACCEL_LBVH) == 0;
+  if (const char* env = getenv("MOX_PLOC_RADIUS")) in.plocRadius = atoi(env);
+  if (const char* env = getenv("MOX_FORCE_LBVH")) { if (atoi(env)) in.usePloc = false; }
   BuildOutput out;
   std::string err;
   if (!buildBvh(in, out, c->stream, err)) return fail(c, MOX_ERR_CUDA, "build_accel: " + err);

@@ -1,0 +1,307 @@
+// ploc.cu — higher-quality hierarchy over the Morton-sorted primitives: parallel locally-ordered
+// clustering (Meister & Bittner 2018).  Starting from one cluster per primitive in Morton order,
+// every iteration (1) finds each cluster's nearest neighbour — smallest merged surface area —
+// within a window of +-radius, (2) merges mutual nearest-neighbour pairs into a new inner node,
+// (3) compacts the cluster array, keeping its order.  The result is a binary tree whose SAH cost
+// is well below the Karras radix tree's (which only looks at Morton prefixes); it then goes
+// through the same emit / leaf-fold / pack stages.  Plays the role OptiX's closed "Trbvh"
+// builder had for the reference (MinimalOptiX.cpp:378,494,534).
+//
+// Node ids: [0, N) leaves (leaf i = i-th primitive in Morton order), [N, 2N-1) inner nodes in
+// creation order (the root is created last).  Ids are assigned by a prefix scan, not by atomics,
+// so the build is deterministic.
+#include "build.h"
+#include "vec.cuh"
+
+namespace {
+
+constexpr int PL_THREADS = 256;
+constexpr int PL_ITEMS = 4;
+constexpr int PL_TILE = PL_THREADS * PL_ITEMS;
+constexpr int PL_MAX_RADIUS = 32;
+
+__device__ __forceinline__ float mergedArea(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi) {
+  float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
+  float dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y);
+  float dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// leaf clusters: id = i, box = box of the i-th sorted primitive
+__global__ void k_ploc_init(int n, const uint32_t* __restrict__ sortedIds, const float4* __restrict__ primLo,
+                            const float4* __restrict__ primHi, uint32_t* __restrict__ cid, float4* __restrict__ cLo,
+                            float4* __restrict__ cHi, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi,
+                            uint32_t* __restrict__ size) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t id = sortedIds[i];
+  float4 lo = primLo[id], hi = primHi[id];
+  cid[i] = (uint32_t)i;
+  cLo[i] = lo; cHi[i] = hi;
+  nodeLo[i] = lo; nodeHi[i] = hi;
+  size[i] = 1u;
+}
+
+// nearest neighbour of cluster i among [i - radius, i + radius]; ties -> smaller index.
+__global__ void __launch_bounds__(PL_THREADS) k_ploc_nn(int n, int radius, const float4* __restrict__ cLo,
+                                                        const float4* __restrict__ cHi, uint32_t* __restrict__ nn) {
+  __shared__ float4 sLo[PL_THREADS + 2 * PL_MAX_RADIUS], sHi[PL_THREADS + 2 * PL_MAX_RADIUS];
+  const int base = blockIdx.x * PL_THREADS - radius;
+  for (int k = threadIdx.x; k < PL_THREADS + 2 * radius; k += PL_THREADS) {
+    int j = base + k;
+    if (j >= 0 && j < n) { sLo[k] = cLo[j]; sHi[k] = cHi[j]; }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * PL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const int me = threadIdx.x + radius;
+  const float4 lo = sLo[me], hi = sHi[me];
+  float best = __int_as_float(0x7f800000);
+  int bestJ = -1;
+  for (int o = -radius; o <= radius; ++o) {
+    int j = i + o;
+    if (o == 0 || j < 0 || j >= n) continue;
+    float a = mergedArea(lo, hi, sLo[me + o], sHi[me + o]);
+    if (a < best) { best = a; bestJ = j; }  // ascending j: the first minimum has the smallest index
+  }
+  nn[i] = (uint32_t)bestJ;
+}
+
+// flags of cluster i: low word = survives compaction (1/0), high word = creates a node (1/0)
+__device__ __forceinline__ unsigned long long plocFlags(int i, int n, const uint32_t* __restrict__ nn) {
+  if (i >= n) return 0ull;
+  int j = (int)nn[i];
+  bool mutual = j >= 0 && (int)nn[j] == i;
+  bool merged = mutual && i < j, removed = mutual && i > j;
+  return (removed ? 0ull : 1ull) | (merged ? (1ull << 32) : 0ull);
+}
+
+__device__ __forceinline__ unsigned long long blockReduce(unsigned long long v, unsigned long long* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (int w = 0; w < PL_THREADS / 32; ++w) t += sh[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(PL_THREADS) k_ploc_tile_sums(int n, const uint32_t* __restrict__ nn,
+                                                               unsigned long long* __restrict__ tileSums) {
+  __shared__ unsigned long long sh[PL_THREADS / 32];
+  unsigned long long v = 0;
+  int base = blockIdx.x * PL_TILE + threadIdx.x * PL_ITEMS;
+#pragma unroll
+  for (int k = 0; k < PL_ITEMS; ++k) v += plocFlags(base + k, n, nn);
+  unsigned long long t = blockReduce(v, sh);
+  if (threadIdx.x == 0) tileSums[blockIdx.x] = t;
+}
+
+// single block: exclusive scan of the tile sums in place; total -> *total
+__global__ void __launch_bounds__(1024) k_ploc_scan_tiles(int nTiles, unsigned long long* __restrict__ tileSums,
+                                                          unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long sh[1024];
+  unsigned long long carry = 0;
+  for (int base = 0; base < nTiles; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned long long v = i < nTiles ? tileSums[i] : 0ull;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0ull;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nTiles) tileSums[i] = carry + sh[threadIdx.x] - v;
+    carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// merge mutual pairs and compact: new cluster arrays, new inner nodes
+__global__ void __launch_bounds__(PL_THREADS)
+k_ploc_merge(int n, int nLeaves, uint32_t nodeBase, const uint32_t* __restrict__ nn, const unsigned long long* __restrict__ tileOffsets,
+             const uint32_t* __restrict__ cidIn, const float4* __restrict__ cLoIn, const float4* __restrict__ cHiIn,
+             uint32_t* __restrict__ cidOut, float4* __restrict__ cLoOut, float4* __restrict__ cHiOut,
+             float4* __restrict__ nodeLo, float4* __restrict__ nodeHi, uint2* __restrict__ children, uint32_t* __restrict__ parent,
+             uint32_t* __restrict__ size) {
+  __shared__ unsigned long long sh[PL_THREADS / 32];
+  __shared__ unsigned long long warpOff[PL_THREADS / 32];
+  const int base = blockIdx.x * PL_TILE + threadIdx.x * PL_ITEMS;
+  unsigned long long f[PL_ITEMS], v = 0;
+#pragma unroll
+  for (int k = 0; k < PL_ITEMS; ++k) { f[k] = plocFlags(base + k, n, nn); v += f[k]; }
+  // exclusive scan of v over the block
+  unsigned long long incl = v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int w = 0; w < PL_THREADS / 32; ++w) { warpOff[w] = run; run += sh[w]; }
+  }
+  __syncthreads();
+  unsigned long long off = tileOffsets[blockIdx.x] + warpOff[warp] + incl - v;
+#pragma unroll
+  for (int k = 0; k < PL_ITEMS; ++k) {
+    int i = base + k;
+    if (i < n && (f[k] & 1ull)) {
+      uint32_t pos = (uint32_t)(off & 0xffffffffull);
+      if (f[k] >> 32) {
+        uint32_t j = nn[i];
+        uint32_t node = nodeBase + (uint32_t)(off >> 32);  // id among inner nodes
+        uint32_t a = cidIn[i], b = cidIn[j];
+        float4 alo = cLoIn[i], ahi = cHiIn[i], blo = cLoIn[j], bhi = cHiIn[j];
+        float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+        float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+        uint32_t id = (uint32_t)nLeaves + node;
+        children[node] = make_uint2(a, b);
+        parent[a] = id; parent[b] = id;
+        size[id] = size[a] + size[b];
+        nodeLo[id] = lo; nodeHi[id] = hi;
+        cidOut[pos] = id; cLoOut[pos] = lo; cHiOut[pos] = hi;
+      } else {
+        cidOut[pos] = cidIn[i]; cLoOut[pos] = cLoIn[i]; cHiOut[pos] = cHiIn[i];
+      }
+    }
+    off += f[k];
+  }
+}
+
+// Position of the leftmost leaf of `node` in depth-first (leaf) order: walking up, every time we
+// are a right child the left sibling's whole subtree precedes us.
+__device__ __forceinline__ uint32_t leftmostPos(uint32_t node, uint32_t root, int nLeaves, const uint32_t* __restrict__ parent,
+                                                const uint2* __restrict__ children, const uint32_t* __restrict__ size) {
+  uint32_t pos = 0;
+  while (node != root) {
+    uint32_t p = parent[node];
+    uint2 ch = children[p - nLeaves];
+    if (ch.y == node) pos += size[ch.x];
+    node = p;
+  }
+  return pos;
+}
+
+__global__ void k_ploc_leaf_order(int nLeaves, uint32_t root, const uint32_t* __restrict__ parent, const uint2* __restrict__ children,
+                                  const uint32_t* __restrict__ size, const uint32_t* __restrict__ sortedIds,
+                                  uint32_t* __restrict__ leafPos, uint32_t* __restrict__ orderedIds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nLeaves) return;
+  uint32_t pos = leftmostPos((uint32_t)i, root, nLeaves, parent, children, size);
+  leafPos[i] = pos;
+  orderedIds[pos] = sortedIds[i];
+}
+
+// Aila–Laine nodes; inner node k (creation order) is written at nInner-1-k so the root is node 0
+// and the top of the tree is contiguous.  Subtrees of <= MOX_LEAF_MAX prims fold into one leaf.
+__global__ void k_ploc_emit(int nLeaves, int nInner, uint32_t root, const uint32_t* __restrict__ parent,
+                            const uint2* __restrict__ children, const uint32_t* __restrict__ size,
+                            const uint32_t* __restrict__ leafPos, const float4* __restrict__ nodeLo,
+                            const float4* __restrict__ nodeHi, BvhNode2* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nInner) return;
+  uint2 ch = children[k];
+  uint32_t c[2] = {ch.x, ch.y};
+  int ref[2];
+  float4 lo[2], hi[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    lo[s] = nodeLo[c[s]]; hi[s] = nodeHi[c[s]];
+    if (c[s] < (uint32_t)nLeaves) {
+      ref[s] = ~((int)(leafPos[c[s]] << 3) | 0);
+    } else {
+      uint32_t cnt = size[c[s]];
+      if (cnt <= MOX_LEAF_MAX) {
+        uint32_t first = leftmostPos(c[s], root, nLeaves, parent, children, size);
+        ref[s] = ~((int)(first << 3) | (int)(cnt - 1));
+      } else {
+        ref[s] = nInner - 1 - (int)(c[s] - nLeaves);
+      }
+    }
+  }
+  BvhNode2 nd;
+  nd.c0xy = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
+  nd.c1xy = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
+  nd.cz = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
+  nd.ref = make_int4(ref[0], ref[1], 0, 0);
+  out[nInner - 1 - k] = nd;
+}
+
+inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+#define PCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+bool plocAlloc(PlocScratch& s, int n, std::string& err) {
+  const size_t nn = (size_t)std::max(n, 2);
+  PCK(cudaMalloc(&s.cid[0], nn * 4)); PCK(cudaMalloc(&s.cid[1], nn * 4));
+  PCK(cudaMalloc(&s.cLo[0], nn * 16)); PCK(cudaMalloc(&s.cLo[1], nn * 16));
+  PCK(cudaMalloc(&s.cHi[0], nn * 16)); PCK(cudaMalloc(&s.cHi[1], nn * 16));
+  PCK(cudaMalloc(&s.nn, nn * 4));
+  PCK(cudaMalloc(&s.nodeLo, 2 * nn * 16)); PCK(cudaMalloc(&s.nodeHi, 2 * nn * 16));
+  PCK(cudaMalloc(&s.children, nn * 8));
+  PCK(cudaMalloc(&s.parent, 2 * nn * 4)); PCK(cudaMalloc(&s.size, 2 * nn * 4));
+  PCK(cudaMalloc(&s.leafPos, nn * 4)); PCK(cudaMalloc(&s.orderedIds, nn * 4));
+  PCK(cudaMalloc(&s.tileSums, (size_t)(divUp(nn, PL_TILE) + 1) * 8));
+  PCK(cudaMallocHost(&s.hostTotal, 8));
+  return true;
+}
+
+void plocFree(PlocScratch& s) {
+  for (int k = 0; k < 2; ++k) { cudaFree(s.cid[k]); cudaFree(s.cLo[k]); cudaFree(s.cHi[k]); }
+  cudaFree(s.nn); cudaFree(s.nodeLo); cudaFree(s.nodeHi); cudaFree(s.children); cudaFree(s.parent); cudaFree(s.size);
+  cudaFree(s.leafPos); cudaFree(s.orderedIds); cudaFree(s.tileSums);
+  if (s.hostTotal) cudaFreeHost(s.hostTotal);
+  s = PlocScratch();
+}
+
+// n >= 2 valid primitives in Morton order (sortedIds); primLo/primHi indexed by primitive id.
+// Writes n-1 nodes to outNodes (root = node 0) and the leaf-ordered ids to s.orderedIds.
+bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* primLo, const float4* primHi, int radius,
+               BvhNode2* outNodes, float rootLo[3], float rootHi[3], cudaStream_t stream, std::string& err) {
+  radius = std::max(1, std::min(radius, PL_MAX_RADIUS));
+  const int B = 256;
+  k_ploc_init<<<divUp(n, B), B, 0, stream>>>(n, sortedIds, primLo, primHi, s.cid[0], s.cLo[0], s.cHi[0], s.nodeLo, s.nodeHi, s.size);
+  int cur = 0, count = n;
+  uint32_t nodeBase = 0;
+  unsigned long long* dTotal = s.tileSums + divUp((size_t)std::max(n, 2), PL_TILE);
+  int guard = 0;
+  while (count > 1) {
+    int nTiles = divUp(count, PL_TILE);
+    k_ploc_nn<<<divUp(count, PL_THREADS), PL_THREADS, 0, stream>>>(count, radius, s.cLo[cur], s.cHi[cur], s.nn);
+    k_ploc_tile_sums<<<nTiles, PL_THREADS, 0, stream>>>(count, s.nn, s.tileSums);
+    k_ploc_scan_tiles<<<1, 1024, 0, stream>>>(nTiles, s.tileSums, dTotal);
+    k_ploc_merge<<<nTiles, PL_THREADS, 0, stream>>>(count, n, nodeBase, s.nn, s.tileSums, s.cid[cur], s.cLo[cur], s.cHi[cur],
+                                                     s.cid[cur ^ 1], s.cLo[cur ^ 1], s.cHi[cur ^ 1], s.nodeLo, s.nodeHi, s.children,
+                                                     s.parent, s.size);
+    PCK(cudaMemcpyAsync(s.hostTotal, dTotal, 8, cudaMemcpyDeviceToHost, stream));
+    PCK(cudaStreamSynchronize(stream));
+    unsigned long long total = *s.hostTotal;
+    int newCount = (int)(total & 0xffffffffull);
+    uint32_t merged = (uint32_t)(total >> 32);
+    if (merged == 0 || newCount != count - (int)merged || ++guard > 4096) { err = "PLOC made no progress"; return false; }
+    nodeBase += merged;
+    count = newCount;
+    cur ^= 1;
+  }
+  const int nInner = n - 1;
+  if ((int)nodeBase != nInner) { err = "PLOC node count mismatch"; return false; }
+  const uint32_t root = (uint32_t)(n + nInner - 1);
+  k_ploc_leaf_order<<<divUp(n, B), B, 0, stream>>>(n, root, s.parent, s.children, s.size, sortedIds, s.leafPos, s.orderedIds);
+  k_ploc_emit<<<divUp(nInner, B), B, 0, stream>>>(n, nInner, root, s.parent, s.children, s.size, s.leafPos, s.nodeLo, s.nodeHi, outNodes);
+  float4 lo, hi;
+  PCK(cudaMemcpyAsync(&lo, s.nodeLo + root, 16, cudaMemcpyDeviceToHost, stream));
+  PCK(cudaMemcpyAsync(&hi, s.nodeHi + root, 16, cudaMemcpyDeviceToHost, stream));
+  PCK(cudaStreamSynchronize(stream));
+  PCK(cudaGetLastError());
+  rootLo[0] = lo.x; rootLo[1] = lo.y; rootLo[2] = lo.z;
+  rootHi[0] = hi.x; rootHi[1] = hi.y; rootHi[2] = hi.z;
+  return true;
+}

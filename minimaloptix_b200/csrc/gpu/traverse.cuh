@@ -214,7 +214,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
         active = false;
       }
       unsigned busy = __ballot_sync(FULL, active);
-      if (busy == 0u || (!exhausted && __popc(busy) < MOX_FETCH_THRESHOLD)) break;
+      if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
     }
   }
 }

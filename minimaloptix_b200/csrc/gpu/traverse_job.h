@@ -18,5 +18,6 @@ struct TraceJob {
   float4* hits;
   float4* shC;
   uint32_t* counters;
+  int fetchThreshold;   // refill idle lanes when fewer than this many lanes are traversing
 };
 

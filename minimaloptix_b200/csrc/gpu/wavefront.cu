@@ -16,6 +16,8 @@
 // carries throughput T and radiance R: R += T*B, T *= A.
 #include "wavefront.h"
 
+#include <cstdlib>
+
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -407,8 +409,16 @@ static unsigned persistentGrid(uint32_t count) {
   return need < full ? need : full;
 }
 
-void launchTraverse(const SceneView& s, const TraceJob& job, bool anyHit, bool count, cudaStream_t stream) {
-  if (!job.count) return;
+static int fetchThreshold() {
+  static int t = -1;
+  if (t < 0) { const char* e = getenv("MOX_FETCH_THRESHOLD"); t = e ? atoi(e) : MOX_FETCH_THRESHOLD; if (t < 1) t = 1; if (t > 32) t = 32; }
+  return t;
+}
+
+void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool count, cudaStream_t stream) {
+  if (!jobIn.count) return;
+  TraceJob job = jobIn;
+  job.fetchThreshold = fetchThreshold();
   cudaMemsetAsync(job.cursor, 0, 4, stream);
   if (anyHit) {
     k_traverse<true, false><<<persistentGrid<true, false>(job.count), TRAV_TPB, 0, stream>>>(s, job);

@@ -86,11 +86,12 @@ def test_closest_hit_cornell_open_front(host, api_tables, orc, gpu_backend):
     assert nbad <= 3
 
 
-def test_closest_hit_interior_mesh(host, api_tables, orc, gpu_backend):
+@pytest.mark.parametrize("flags", [S.ACCEL_DEFAULT, S.ACCEL_LBVH], ids=["ploc", "lbvh"])
+def test_closest_hit_interior_mesh(host, api_tables, orc, gpu_backend, flags):
     sc = host.Scene.builtin("interior", 60000)
     info = sc.info()
     assert 40000 < info.n_triangles < 90000
-    o, g = both(host, api_tables, orc, gpu_backend, sc, 64, 64, 5)  # oracle BVH for speed
+    o, g = both(host, api_tables, orc, gpu_backend, sc, 64, 64, 5, flags=flags)  # oracle BVH for speed
     rays = random_rays(400000, [0.05, 0.05, 0.05], [9.95, 3.95, 7.95], 4)
     nbad, nhit = check_ids(o, g, rays, "interior")
     assert nhit == len(rays)
@@ -103,9 +104,10 @@ def test_closest_hit_interior_mesh(host, api_tables, orc, gpu_backend):
     assert nbad <= 2
 
 
-def test_closest_hit_soup(host, api_tables, orc, gpu_backend):
+@pytest.mark.parametrize("flags", [S.ACCEL_DEFAULT, S.ACCEL_LBVH], ids=["ploc", "lbvh"])
+def test_closest_hit_soup(host, api_tables, orc, gpu_backend, flags):
     sc = host.Scene.builtin("soup", 200000, 7)
-    o, g = both(host, api_tables, orc, gpu_backend, sc, 64, 64, 5)
+    o, g = both(host, api_tables, orc, gpu_backend, sc, 64, 64, 5, flags=flags)
     rays = random_rays(300000, [0, 0, 0], [1, 1, 1], 5)
     nbad, nhit = check_ids(o, g, rays, "soup")
     assert nhit > 150000
