@@ -373,7 +373,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out = BuildOutput();
   if (n == 0) {  // empty scene: a root with two empty children
     BvhNode2 root;
-    root.c0xy = root.c1xy = root.cz = make_float4(0, 0, 0, 0);
+    root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);  // empty children: a point box no ray reaches
     root.ref = make_int4(MOX_EMPTY_CHILD, MOX_EMPTY_CHILD, 0, 0);
     CK(cudaMalloc(&out.nodes, sizeof(BvhNode2)));
     CK(cudaMalloc(&out.packed, 48));
@@ -453,7 +453,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, out.packed);
   if (nValid <= 1) {
     BvhNode2 root;
-    root.c0xy = root.c1xy = root.cz = make_float4(0, 0, 0, 0);
+    root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);
     root.ref = make_int4(MOX_EMPTY_CHILD, MOX_EMPTY_CHILD, 0, 0);
     if (nValid == 1) {
       uint32_t firstId = 0;
@@ -462,7 +462,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
       CKB(cudaMemcpy(&lo, boxLo + firstId, 16, cudaMemcpyDeviceToHost));
       CKB(cudaMemcpy(&hi, boxHi + firstId, 16, cudaMemcpyDeviceToHost));
       root.c0xy = make_float4(lo.x, hi.x, lo.y, hi.y);
-      root.cz = make_float4(lo.z, hi.z, 0, 0);
+      root.cz = make_float4(lo.z, hi.z, MOX_FAR, MOX_FAR);
       root.ref.x = ~((0 << 3) | 0);
       out.sceneLo[0] = lo.x; out.sceneLo[1] = lo.y; out.sceneLo[2] = lo.z;
       out.sceneHi[0] = hi.x; out.sceneHi[1] = hi.y; out.sceneHi[2] = hi.z;

@@ -178,7 +178,7 @@ void freePaths(PathBuffers& pb) {
   cudaFree(pb.rayO); cudaFree(pb.rayD); cudaFree(pb.hit); cudaFree(pb.thr); cudaFree(pb.rad); cudaFree(pb.state);
   cudaFree(pb.qCur); cudaFree(pb.qNext);
   for (auto& q : pb.qMat) cudaFree(q);
-  cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.counters); cudaFree(pb.seeds);
+  cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.shQueue); cudaFree(pb.counters); cudaFree(pb.seeds);
   pb = PathBuffers();
 }
 
@@ -198,7 +198,8 @@ int ensurePaths(mox_ctx* c, size_t paths, size_t nLights, size_t nSeeds) {
     CUCK(c, cudaMalloc(&pb.qCur, paths * 4)); CUCK(c, cudaMalloc(&pb.qNext, paths * 4));
     for (auto& q : pb.qMat) CUCK(c, cudaMalloc(&q, paths * 4));
     if (slots) {
-      CUCK(c, cudaMalloc(&pb.shO, slots * 16)); CUCK(c, cudaMalloc(&pb.shD, slots * 16)); CUCK(c, cudaMalloc(&pb.shC, slots * 16));
+      CUCK(c, cudaMalloc(&pb.shO, paths * 16)); CUCK(c, cudaMalloc(&pb.shD, slots * 16)); CUCK(c, cudaMalloc(&pb.shC, slots * 16));
+      CUCK(c, cudaMalloc(&pb.shQueue, slots * 4));
     }
     CUCK(c, cudaMalloc(&pb.counters, C_WORDS * 4));
     CUCK(c, cudaMemset(pb.counters, 0, C_WORDS * 4));
@@ -690,7 +691,7 @@ int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* d
   CUCK(c, cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream));
   launchSplitRays((const float4*)dev_rays, (float4*)c->dQueryO.p, (float4*)c->dQueryD.p, n, c->stream);
   TraceJob job;
-  job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n;
+  job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n; job.countPtr = nullptr; job.originMod = 0;
   job.cursor = counters + C_CURSOR; job.hits = (float4*)dev_hits; job.shC = nullptr; job.counters = counters;
   CUCK(c, cudaMemsetAsync(job.cursor, 0, 4, c->stream));
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
@@ -752,7 +753,7 @@ int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
   launchSplitRays((const float4*)dRays, (float4*)c->dQueryO.p, (float4*)c->dQueryD.p, n, c->stream);
   launchFillOnes((float4*)dC, n, c->stream);
   TraceJob job;
-  job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n;
+  job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n; job.countPtr = nullptr; job.originMod = 0;
   job.cursor = counters + C_CURSOR; job.hits = nullptr; job.shC = (float4*)dC; job.counters = counters;
   launchTraverse(sceneView(c), job, true, false, c->stream);
   launchCopyRgb((const float4*)dC, (float*)dOut, n, c->stream);

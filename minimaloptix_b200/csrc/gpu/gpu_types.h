@@ -33,10 +33,12 @@ struct __align__(16) Analytic { float4 a, b, c, d; };
 //   c0xy = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   c1xy likewise
 //   cz   = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //   ref  = (child0, child1, -, -): >= 0 inner node index; < 0 leaf: ~((first << 3) | (count - 1))
-//          over the leaf-ordered packed primitive array; 0x80000000 = empty child.
+//          over the leaf-ordered packed primitive array; 0x80000000 = empty child (its box is the
+//          point (MOX_FAR, MOX_FAR, MOX_FAR), which no ray reaches, so the hot loop never tests for it).
 struct __align__(16) BvhNode2 { float4 c0xy, c1xy, cz; int4 ref; };
 static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 #define MOX_EMPTY_CHILD ((int)0x80000000)
+#define MOX_FAR 3.0e38f   // box coordinates of an empty child: every slab test misses it
 #define MOX_LEAF_MAX 4
 
 // Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.

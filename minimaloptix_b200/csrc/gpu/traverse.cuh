@@ -78,12 +78,15 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
 #define MOX_DONE ((int)0x80000000)   // sentinel "no more nodes" (same bit pattern as an empty child)
 #define MOX_FETCH_THRESHOLD 20       // refill a warp's idle lanes when fewer than this many are traversing
 
-// Persistent-thread while-while traversal (Aila & Laine 2009) over the binary BVH.
+// Persistent-thread traversal over the binary BVH with warp-level phase voting.
 //   * warps fetch rays from a global cursor: 32 at start, then whenever fewer than
-//     MOX_FETCH_THRESHOLD lanes are still traversing the idle lanes are refilled;
-//   * inner loop descends inner nodes until the lane reaches a leaf, then the leaf's
-//     primitives are tested (closest hit: (t, id) lexicographic; any hit: Disney prims only,
-//     NORMAL blocks, GLASS tints — SURVEY.md §8 a-11, Material.cu:225-232);
+//     job.fetchThreshold lanes are still busy the idle lanes are refilled (Aila & Laine 2009);
+//   * every iteration the warp votes: if at least as many lanes sit at an inner node as at a leaf
+//     it runs ONE inner-node step (two child slabs, near child first), otherwise ONE primitive
+//     test for the lanes inside a leaf.  The branch is warp-uniform, so the executing phase always
+//     has at least half of the busy lanes active — a plain while-while loop measured 10 of 32;
+//   * closest hit obeys the (t, id) lexicographic rule; any hit: Disney prims only, NORMAL
+//     blocks, GLASS tints (Material.cu:225-232);
 //   * per-lane traversal stack in local memory (far children only).
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const TraceJob& job) {
@@ -91,8 +94,10 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
   const float INF = __int_as_float(0x7f800000);
+  const uint32_t jobCount = job.countPtr ? __ldg(job.countPtr) : job.count;
   int stack[MOX_STACK];
   int sp = 0, cur = MOX_DONE;
+  uint32_t lk = 0, lend = 0;  // primitive cursor inside the current leaf
   bool active = false, exhausted = false;
   uint32_t rayId = 0;
   RayPre r;
@@ -101,6 +106,15 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
   int bPrim = -1;
   float3 atten = mk3(1.f);
   uint32_t nv = 0, np = 0;
+
+#define MOX_SET_CUR(c)                                             \
+  do {                                                             \
+    cur = (c);                                                     \
+    if (cur < 0 && cur != MOX_DONE) {                              \
+      uint32_t leaf_ = (uint32_t)~cur;                             \
+      lk = leaf_ >> 3; lend = lk + (leaf_ & 7u) + 1u;              \
+    }                                                              \
+  } while (0)
 
   while (true) {
     // ---------------- refill idle lanes
@@ -113,9 +127,10 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
         base = __shfl_sync(FULL, base, leader);
         if (!active) {
           uint32_t i = base + __popc(idle & ltMask);
-          if (i < job.count) {
+          if (i < jobCount) {
             rayId = job.queue ? __ldg(job.queue + i) : i;
-            float4 ro = __ldg(job.rayO + rayId), rd = __ldg(job.rayD + rayId);
+            uint32_t oId = job.originMod ? rayId % job.originMod : rayId;
+            float4 ro = __ldg(job.rayO + oId), rd = __ldg(job.rayD + rayId);
             if (!(ANYHIT && rd.w < 0.f)) {
               r = prepRay(mk3(ro), mk3(rd), ro.w);
               tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
@@ -126,43 +141,44 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
             }
           }
         }
-        if (base + __popc(idle) >= job.count) exhausted = true;
+        if (base + __popc(idle) >= jobCount) exhausted = true;
       }
     }
     if (!__any_sync(FULL, active)) {
       if (exhausted) break;
       continue;
     }
-    // ---------------- traverse until too few lanes are busy.  Every lane runs the same
-    // skeleton (idle lanes hold cur == MOX_DONE) so the two __syncwarp()s are legal; they force
-    // the warp to reconverge between the inner-node loop and the leaf tests — without them the
-    // lanes drift through the leaf code one by one (measured: 1.5 threads per instruction).
+    // ---------------- traverse until too few lanes are busy
     while (true) {
-      while (cur >= 0) {  // inner nodes
-        const BvhNode2* nd = s.nodes + cur;
-        float4 a = __ldg(&nd->c0xy), b = __ldg(&nd->c1xy), z = __ldg(&nd->cz);
-        int4 ref = __ldg(&nd->ref);
-        if (COUNT) nv++;
-        float t0 = ref.x == MOX_EMPTY_CHILD ? INF : boxEntry(r, a.x, a.y, a.z, a.w, z.x, z.y, tBest);
-        float t1 = ref.y == MOX_EMPTY_CHILD ? INF : boxEntry(r, b.x, b.y, b.z, b.w, z.z, z.w, tBest);
-        bool h0 = t0 < INF, h1 = t1 < INF;
-        if (h0 && h1) {
-          bool swp = t1 < t0;
-          if (sp < MOX_STACK) stack[sp++] = swp ? ref.x : ref.y;
-          cur = swp ? ref.y : ref.x;
-        } else if (h0 || h1) {
-          cur = h0 ? ref.x : ref.y;
-        } else {
-          cur = sp ? stack[--sp] : MOX_DONE;
+      const bool isInner = cur >= 0;
+      const bool isLeaf = !isInner && cur != MOX_DONE;
+      const unsigned im = __ballot_sync(FULL, isInner), lm = __ballot_sync(FULL, isLeaf);
+      const unsigned busy = im | lm;
+      if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
+      if (__popc(im) >= __popc(lm)) {
+        if (isInner) {  // one inner-node step
+          const BvhNode2* nd = s.nodes + cur;
+          float4 a = __ldg(&nd->c0xy), b = __ldg(&nd->c1xy), z = __ldg(&nd->cz);
+          int4 ref = __ldg(&nd->ref);
+          if (COUNT) nv++;
+          float t0 = boxEntry(r, a.x, a.y, a.z, a.w, z.x, z.y, tBest);
+          float t1 = boxEntry(r, b.x, b.y, b.z, b.w, z.z, z.w, tBest);
+          bool h0 = t0 < INF, h1 = t1 < INF;
+          int next;
+          if (h0 && h1) {
+            bool swp = t1 < t0;
+            stack[sp++] = swp ? ref.x : ref.y;
+            next = swp ? ref.y : ref.x;
+          } else if (h0 || h1) {
+            next = h0 ? ref.x : ref.y;
+          } else {
+            next = sp ? stack[--sp] : MOX_DONE;
+          }
+          MOX_SET_CUR(next);
         }
-      }
-      __syncwarp();
-      if (cur != MOX_DONE) {  // leaf
-        uint32_t leaf = (uint32_t)~cur;
-        uint32_t first = leaf >> 3, count = (leaf & 7u) + 1u;
-        bool blocked = false;
-        for (uint32_t k = 0; k < count; ++k) {
-          const float4* rec = s.packed + (size_t)(first + k) * MOX_PACKED_F4;
+      } else {
+        if (isLeaf) {  // one primitive test
+          const float4* rec = s.packed + (size_t)lk * MOX_PACKED_F4;
           float4 r0 = __ldg(rec);
           if (COUNT) np++;
           uint32_t idbits = __float_as_uint(r0.w);
@@ -183,23 +199,24 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
               hit = quadTest(q, r.o, r.d, r.tmin, t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
             }
           }
+          bool blocked = false;
           if (hit) {
             if (ANYHIT) {
               // geometry first, material only on a hit: non-Disney prims do not occlude shadow rays
               const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
               if (__ldg(&m->kind) == MOX_MAT_DISNEY) {
                 if (__ldg((const int*)&m->dis.brdfType) == GLASS) atten *= mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
-                else { blocked = true; break; }
+                else { blocked = true; atten = mk3(0.f); }
               }
             } else {
               tBest = t; bPrim = id; bBeta = be; bGamma = ga;
             }
           }
+          ++lk;
+          if (blocked) cur = MOX_DONE;
+          else if (lk == lend) { int next = sp ? stack[--sp] : MOX_DONE; MOX_SET_CUR(next); }
         }
-        cur = (blocked || sp == 0) ? MOX_DONE : stack[--sp];
-        if (ANYHIT && blocked) atten = mk3(0.f);
       }
-      __syncwarp();
       if (active && cur == MOX_DONE) {  // ray finished
         if (ANYHIT) {
           float4 c = job.shC[rayId];
@@ -213,8 +230,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
         }
         active = false;
       }
-      unsigned busy = __ballot_sync(FULL, active);
-      if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
     }
   }
+#undef MOX_SET_CUR
 }

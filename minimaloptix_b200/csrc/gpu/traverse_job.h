@@ -14,6 +14,8 @@ struct TraceJob {
   const float4* rayD;
   const uint32_t* queue;
   uint32_t count;
+  const uint32_t* countPtr;  // when set, the ray count is read from device memory instead
+  uint32_t originMod;        // when non-zero, the origin of ray id is rayO[id % originMod]
   uint32_t* cursor;
   float4* hits;
   float4* shC;

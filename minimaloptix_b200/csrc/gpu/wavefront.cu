@@ -300,10 +300,14 @@ __global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t coun
     float3 pc = Tprev * contrib;
     // a zero contribution needs no shadow ray (it is still counted, as the reference traces it)
     bool trace = pc.x != 0.f || pc.y != 0.f || pc.z != 0.f;
-    c.pb.shO[slot] = make_float4(a.front.x, a.front.y, a.front.z, c.rp.eps);
-    c.pb.shD[slot] = make_float4(L.x, L.y, L.z, trace ? lightDst - c.rp.eps : -1.f);
     c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
+    if (trace) {
+      c.pb.shD[slot] = make_float4(L.x, L.y, L.z, lightDst - c.rp.eps);
+      uint32_t pos = queuePush(c.pb.counters + C_SHQ);
+      c.pb.shQueue[pos] = (uint32_t)slot;
+    }
   }
+  if (nL) c.pb.shO[i] = make_float4(a.front.x, a.front.y, a.front.z, c.rp.eps);  // one origin for all lights of this hit
   if (shadowCount) atomicAdd(c.pb.counters + C_SHADOW, shadowCount);
   {  // + emission
     float3 e = f3(dp.emission);
@@ -432,7 +436,7 @@ void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool
 void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
   if (!count) return;
   TraceJob job;
-  job.rayO = c.pb.rayO; job.rayD = c.pb.rayD; job.queue = queue; job.count = count;
+  job.rayO = c.pb.rayO; job.rayD = c.pb.rayD; job.queue = queue; job.count = count; job.countPtr = nullptr; job.originMod = 0;
   job.cursor = c.pb.counters + C_CURSOR; job.hits = c.pb.hit; job.shC = nullptr; job.counters = c.pb.counters;
   launchTraverse(c.scene, job, false, c.countTraversal, c.stream);
 }
@@ -452,7 +456,9 @@ void launchShadow(const LaunchCtx& c, uint32_t disneyCount) {
   if (!disneyCount || c.scene.nLights == 0) return;
   size_t slots = (size_t)disneyCount * c.scene.nLights;
   TraceJob job;
-  job.rayO = c.pb.shO; job.rayD = c.pb.shD; job.queue = nullptr; job.count = (uint32_t)slots;
+  // dense queue of the slots that need a ray; its length lives in device memory (no host sync)
+  job.rayO = c.pb.shO; job.rayD = c.pb.shD; job.queue = c.pb.shQueue; job.count = (uint32_t)slots;
+  job.countPtr = c.pb.counters + C_SHQ; job.originMod = disneyCount;
   job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
   launchTraverse(c.scene, job, true, false, c.stream);
 }

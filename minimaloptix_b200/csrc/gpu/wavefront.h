@@ -10,7 +10,7 @@
 enum ShadeQueue { Q_LAMBERT = 0, Q_METAL = 1, Q_DIELECTRIC = 2, Q_DISNEY = 3, Q_COUNT = 4 };
 
 // Device counters (uint32 words).
-enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
+enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_SHQ = 5 /* shadow queue length */, C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
                    C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_WORDS = 16 };
 
 struct PathBuffers {
@@ -20,7 +20,8 @@ struct PathBuffers {
   int* state = nullptr;
   uint32_t *qCur = nullptr, *qNext = nullptr;
   uint32_t* qMat[Q_COUNT] = {nullptr, nullptr, nullptr, nullptr};
-  float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;
+  float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;  // shadow rays: origin per Disney path, (dir, tmax) and contribution per slot
+  uint32_t* shQueue = nullptr;                            // slots that need a shadow ray
   uint32_t* counters = nullptr;   // C_WORDS
   int32_t* seeds = nullptr;       // launch seed per sample of the batch
   size_t seedCap = 0;
