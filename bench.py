@@ -153,6 +153,7 @@ def main():
     import torch.distributed as dist
     import minimaloptix_b200 as mox
     from minimaloptix_b200 import host
+    from minimaloptix_b200.parallel import TileGather
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -174,21 +175,8 @@ def main():
     build_ms = ctx.build_accel()
     cam = sc.cam_params(W, H)
 
-    owned = [ctx.owned_pixels(r) for r in range(world)]
-    pad = max(owned)
-    pack = torch.zeros(pad * 3, dtype=torch.float32, device=dev)
-    gathered = [torch.zeros(pad * 3, dtype=torch.float32, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-
-    def gather():
-        """Final exchange: every rank's owned pixels to rank 0, scattered into its full image."""
-        if world == 1:
-            return
-        ctx.pack_owned(pack.data_ptr())
-        dist.gather(pack, gathered, dst=0)
-        if rank == 0:
-            torch.cuda.synchronize()
-            for r in range(1, world):
-                ctx.unpack_owned(r, gathered[r].data_ptr())
+    tiles = TileGather(ctx, rank, world, dev)
+    gather = tiles.gather  # final exchange: every rank's owned pixels to rank 0 (NCCL gather)
 
     def barrier():
         if world > 1:
@@ -207,6 +195,7 @@ def main():
     # ---- resident run: W warm-up steps, K timed steps + the gather
     for _ in range(args.warmup):
         step()
+    gather()  # warm-up of the exchange too (NCCL communicator set-up happens on the first collective)
     barrier()
     s0 = ctx.stats()
     sampler = ClockSampler(local)
@@ -312,7 +301,7 @@ def main():
                 "spp_per_s": args.steps / (dev_ms * 1e-3), "mshadow_per_s": shadow_all / (dev_ms * 1e3), "bvh_build_ms": build_ms,
                 "wall_ms_per_step": wall_ms / args.steps, "stage_ms": stage_ms,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 76 + 4, "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gather_bytes": tiles.bytes_on_the_wire(), "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
