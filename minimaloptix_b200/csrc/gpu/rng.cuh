@@ -29,43 +29,61 @@ MOX_D void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-struct Rng {
-  int mode;         // 0 REF, 1 PHILOX
-  int state;        // REF: LCG seed; PHILOX: draw counter within the current depth stream
-  uint32_t pixel, launchSeed, depth;
-  uint32_t cache[4];
-  uint32_t cachedBlock;  // PHILOX: which 4-draw block `cache` holds (0xffffffff = none)
+// MODE is a compile-time parameter of the kernels so the REF instantiation carries a single
+// register of generator state.
+template <int MODE>
+struct RngT;
 
+template <>
+struct RngT<0> {  // REF
+  int state;
   MOX_D uint32_t next24() {
-    if (mode == 0) {
-      state = (int)(1664525u * (uint32_t)state + 1013904223u);
-      return (uint32_t)state & 0x00FFFFFFu;
-    }
+    state = (int)(1664525u * (uint32_t)state + 1013904223u);
+    return (uint32_t)state & 0x00FFFFFFu;
+  }
+  MOX_D float rnd() { return (float)next24() / (float)0x01000000; }
+  // State of the child path spawned at depth `childDepth` (computed from the CURRENT state).
+  MOX_D int forkState(int childDepth) const { return (int)tea16((uint32_t)state, (uint32_t)childDepth); }
+};
+
+template <>
+struct RngT<1> {  // PHILOX
+  int state;  // draw counter within the current depth stream
+  uint32_t pixel, launchSeed, depth;
+  uint32_t c0, c1, c2, c3;
+  uint32_t cachedBlock;
+  MOX_D uint32_t next24() {
     uint32_t ctr = (uint32_t)state;
     uint32_t blk = ctr >> 2;
-    if (blk != cachedBlock) { philox4x32_10(blk, depth, 0u, 0u, pixel, launchSeed, cache); cachedBlock = blk; }
-    uint32_t w = (ctr & 3u) == 0 ? cache[0] : (ctr & 3u) == 1 ? cache[1] : (ctr & 3u) == 2 ? cache[2] : cache[3];
+    if (blk != cachedBlock) {
+      uint32_t o[4];
+      philox4x32_10(blk, depth, 0u, 0u, pixel, launchSeed, o);
+      c0 = o[0]; c1 = o[1]; c2 = o[2]; c3 = o[3];
+      cachedBlock = blk;
+    }
+    uint32_t w = (ctr & 3u) == 0 ? c0 : (ctr & 3u) == 1 ? c1 : (ctr & 3u) == 2 ? c2 : c3;
     state = (int)(ctr + 1u);
     return w >> 8;
   }
   MOX_D float rnd() { return (float)next24() / (float)0x01000000; }
-
-  // State of the child path spawned at depth `childDepth` (computed from the CURRENT state).
-  MOX_D int forkState(int childDepth) const {
-    return mode == 0 ? (int)tea16((uint32_t)state, (uint32_t)childDepth) : 0;
-  }
+  MOX_D int forkState(int) const { return 0; }
 };
 
-MOX_D Rng makeRng(int mode, int state, uint32_t pixel, uint32_t launchSeed, uint32_t depth) {
-  Rng r;
-  r.mode = mode; r.state = state; r.pixel = pixel; r.launchSeed = launchSeed; r.depth = depth;
-  r.cachedBlock = 0xffffffffu;
-  r.cache[0] = r.cache[1] = r.cache[2] = r.cache[3] = 0;
+template <int MODE>
+MOX_D RngT<MODE> makeRng(int state, uint32_t pixel, uint32_t launchSeed, uint32_t depth);
+template <>
+MOX_D RngT<0> makeRng<0>(int state, uint32_t, uint32_t, uint32_t) { RngT<0> r; r.state = state; return r; }
+template <>
+MOX_D RngT<1> makeRng<1>(int state, uint32_t pixel, uint32_t launchSeed, uint32_t depth) {
+  RngT<1> r;
+  r.state = state; r.pixel = pixel; r.launchSeed = launchSeed; r.depth = depth;
+  r.c0 = r.c1 = r.c2 = r.c3 = 0; r.cachedBlock = 0xffffffffu;
   return r;
 }
 
 // utils_device.h:36-52 with the draw order pinned x, y, z.
-MOX_D float3 randInUnitSphere(Rng& r) {
+template <class R>
+MOX_D float3 randInUnitSphere(R& r) {
   float3 p;
   do {
     float a = r.rnd(), b = r.rnd(), c = r.rnd();
@@ -73,7 +91,8 @@ MOX_D float3 randInUnitSphere(Rng& r) {
   } while (length(p) >= 1.0f);
   return p;
 }
-MOX_D float3 randInUnitDisk(Rng& r) {
+template <class R>
+MOX_D float3 randInUnitDisk(R& r) {
   float3 p;
   do {
     float a = r.rnd(), b = r.rnd();

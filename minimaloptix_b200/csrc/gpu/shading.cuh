@@ -62,7 +62,8 @@ MOX_D float smithGGgxAniso(float NdotV, float VdotX, float VdotY, float ax, floa
 MOX_D float powerHeuristic(float a, float b) { float t = a * a; return t / (b * b + t); }
 
 // disney.h:9-30; draws: lobe, then (u1,u2) | (phi, xi).
-MOX_D void disneySample(Rng& rng, const DisneyParams& mp, const float3& N, float3& L, const float3& V, float3& H) {
+template <class R>
+MOX_D void disneySample(R& rng, const DisneyParams& mp, const float3& N, float3& L, const float3& V, float3& H) {
   float diffuseRatio = 0.5f * (1.0f - mp.metallic);
   Onb3 onb(N);
   float r0 = rng.rnd();
@@ -87,6 +88,68 @@ MOX_D void disneySample(Rng& rng, const DisneyParams& mp, const float3& N, float
     H = normalize(H);
   }
 }
+
+// Everything in disneyPdf / disneyEval that depends only on the material, the base colour and
+// the shading normal — evaluated once per hit and reused for every light and for the sampled
+// direction.  Same operations in the same order as evaluating the reference functions from
+// scratch each time, so the results are bit-identical.
+struct DisneyHit {
+  float3 N, X, Y, Cdlin, Cspec0, Csheen;
+  float metallic, subsurface, roughness, sheen, clearcoat, ax, ay, clearcoatAlpha, specularAlpha, diffuseRatio, pdfRatio;
+
+  MOX_D DisneyHit(const DisneyParams& mp, const float3& baseColor, const float3& n) {
+    N = n;
+    Onb3 onb(N);
+    Cdlin = mk3(powf(baseColor.x, 2.2f), powf(baseColor.y, 2.2f), powf(baseColor.z, 2.2f));
+    float Cdlum = dot(Cdlin, mk3(0.3f, 0.6f, 0.1f));
+    float3 Ctint = Cdlum > 0.f ? Cdlin / Cdlum : mk3(1.f);
+    Cspec0 = lerp3(mp.specular * 0.08f * lerp3(mk3(1.f), Ctint, mp.specularTint), Cdlin, mp.metallic);
+    Csheen = lerp3(mk3(1.f), Ctint, mp.sheenTint);
+    float aspect = sqrtf(1 - mp.anisotropic * 0.9f);
+    ax = fmaxf(.001f, sqr(mp.roughness) / aspect);
+    ay = fmaxf(.001f, sqr(mp.roughness) * aspect);
+    X = normalize(onb.tangent);
+    Y = normalize(cross(N, X));
+    metallic = mp.metallic; subsurface = mp.subsurface; roughness = mp.roughness; sheen = mp.sheen; clearcoat = mp.clearcoat;
+    clearcoatAlpha = lerpf(0.1f, 0.001f, mp.clearcoatGloss);
+    specularAlpha = fmaxf(0.001f, mp.roughness);
+    diffuseRatio = 0.5f * (1.0f - mp.metallic);
+    pdfRatio = 1.0f / (1.0f + mp.clearcoat);
+  }
+
+  // disney.h:32-46
+  MOX_D float pdf(const float3& L, const float3& H) const {
+    float specularRatio = 1.f - diffuseRatio;
+    float cosTheta = fabsf(dot(N, H));
+    float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha) * cosTheta;
+    float pdfGTR2 = GTR2(cosTheta, specularAlpha) * cosTheta;
+    float pdfH = lerpf(pdfGTR1, pdfGTR2, pdfRatio);
+    float pdfL = pdfH / (4.0f * fabsf(dot(L, H)));
+    float pdfDiff = fabsf(dot(N, L)) / MOX_PI_F;
+    return diffuseRatio * pdfDiff + specularRatio * pdfL;
+  }
+
+  // disney.h:48-91
+  MOX_D float3 eval(const float3& L, const float3& V, const float3& H) const {
+    float NdotL = dot(N, L), NdotV = dot(N, V), NdotH = dot(N, H), LdotH = dot(L, H);
+    float FL = schlickFresnel(NdotL), FV = schlickFresnel(NdotV);
+    float Fd90 = 0.5f + 2.f * LdotH * LdotH * roughness;
+    float Fd = lerpf(1.f, Fd90, FL) * lerpf(1.f, Fd90, FV);
+    float Fss90 = LdotH * LdotH * roughness;
+    float Fss = lerpf(1.0f, Fss90, FL) * lerpf(1.0f, Fss90, FV);
+    float ss = 1.25f * (Fss * (1.f / (NdotL + NdotV) - 0.5f) + 0.5f);
+    float Ds = GTR2Aniso(NdotH, dot(H, X), dot(H, Y), ax, ay);
+    float FH = schlickFresnel(LdotH);
+    float3 Fs = lerp3(Cspec0, mk3(1.f), FH);
+    float Gs = smithGGgxAniso(NdotL, dot(L, X), dot(L, Y), ax, ay) * smithGGgxAniso(NdotV, dot(V, X), dot(V, Y), ax, ay);
+    float3 Fsheen = FH * sheen * Csheen;
+    float Dr = GTR1(NdotH, clearcoatAlpha);
+    float Fr = lerpf(0.04f, 1.f, FH);
+    float Gr = smithGGgx(NdotL, 0.25f) * smithGGgx(NdotV, 0.25f);
+    return ((1.0f / MOX_PI_F) * lerpf(Fd, ss, subsurface) * Cdlin + Fsheen) * (1.0f - metallic) + Gs * Fs * Ds +
+           mk3(0.25f * clearcoat * Gr * Fr * Dr);
+  }
+};
 
 MOX_D float disneyPdf(const DisneyParams& mp, const float3& N, const float3& L, const float3& H) {
   float diffuseRatio = 0.5f * (1.0f - mp.metallic);

@@ -51,14 +51,15 @@ __device__ __forceinline__ PathCtx pathCtx(const LaunchCtx& c, uint32_t path) {
 }
 
 // ------------------------------------------------------------------ generate (Camera.cu:21-36)
+template <int RM>
 __global__ void __launch_bounds__(TPB) k_generate(LaunchCtx c, uint32_t nPaths) {
   uint32_t p = blockIdx.x * TPB + threadIdx.x;
   if (p >= nPaths) return;
   PathCtx pc = pathCtx(c, p);
   const RenderParams& rp = c.rp;
   uint32_t x = pc.pixel % rp.W, y = pc.pixel / rp.W;
-  int st = rp.rngMode == 0 ? (int)tea16(pc.pixel, (uint32_t)pc.launchSeed) : 0;
-  Rng rng = makeRng(rp.rngMode, st, pc.pixel, (uint32_t)pc.launchSeed, 1u);
+  int st = RM == 0 ? (int)tea16(pc.pixel, (uint32_t)pc.launchSeed) : 0;
+  RngT<RM> rng = makeRng<RM>(st, pc.pixel, (uint32_t)pc.launchSeed, 1u);
   const CamParams& cp = rp.cam;
   float3 lens = cp.lensRadius * randInUnitDisk(rng);
   float3 offset = f3(cp.u) * lens.x + f3(cp.v) * lens.y;
@@ -176,25 +177,31 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
   return a;
 }
 
+template <int RM>
 struct ShadeIn {
   uint32_t path;
   float3 o, d;
   float t, beta, gamma;
   PrimDesc pd;
   const GpuMaterial* m;
-  Rng rng;
+  RngT<RM> rng;
 };
 
-__device__ __forceinline__ ShadeIn loadShadeIn(const LaunchCtx& c, uint32_t path, uint32_t depth) {
-  ShadeIn s;
+template <int RM>
+__device__ __forceinline__ ShadeIn<RM> loadShadeIn(const LaunchCtx& c, uint32_t path, uint32_t depth) {
+  ShadeIn<RM> s;
   s.path = path;
   float4 ro = c.pb.rayO[path], rd = c.pb.rayD[path], h = c.pb.hit[path];
   s.o = mk3(ro); s.d = mk3(rd);
   s.t = h.x; s.beta = h.z; s.gamma = h.w;
   s.pd = c.scene.prims[__float_as_int(h.y)];
   s.m = c.scene.mats + (s.pd.typeMat >> 2);
-  PathCtx pc = pathCtx(c, path);
-  s.rng = makeRng(c.rp.rngMode, c.pb.state[path], pc.pixel, (uint32_t)pc.launchSeed, depth);
+  if (RM == 0) {
+    s.rng = makeRng<RM>(c.pb.state[path], 0u, 0u, depth);
+  } else {
+    PathCtx pc = pathCtx(c, path);
+    s.rng = makeRng<RM>(c.pb.state[path], pc.pixel, (uint32_t)pc.launchSeed, depth);
+  }
   return s;
 }
 
@@ -211,11 +218,11 @@ __device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const f
 }
 
 // lambertian (Material.cu:28-43) and metal (:49-66)
-template <bool METAL>
+template <bool METAL, int RM>
 __global__ void __launch_bounds__(TPB) k_shade_diffuse(LaunchCtx c, uint32_t count, uint32_t depth) {
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
-  ShadeIn s = loadShadeIn(c, c.pb.qMat[METAL ? Q_METAL : Q_LAMBERT][i], depth);
+  ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[METAL ? Q_METAL : Q_LAMBERT][i], depth);
   Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, false);
   float3 v = randInUnitSphere(s.rng);
   float3 dir, albedo;
@@ -230,10 +237,11 @@ __global__ void __launch_bounds__(TPB) k_shade_diffuse(LaunchCtx c, uint32_t cou
 }
 
 // glass (Material.cu:72-110) and disney/GLASS (:134-168)
+template <int RM>
 __global__ void __launch_bounds__(TPB) k_shade_dielectric(LaunchCtx c, uint32_t count, uint32_t depth) {
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
-  ShadeIn s = loadShadeIn(c, c.pb.qMat[Q_DIELECTRIC][i], depth);
+  ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DIELECTRIC][i], depth);
   Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, true);
   float ior;
   float3 tint;
@@ -256,15 +264,18 @@ __global__ void __launch_bounds__(TPB) k_shade_dielectric(LaunchCtx c, uint32_t 
 }
 
 // disney/NORMAL (Material.cu:170-222)
-__global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
-  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+constexpr int DISNEY_TPB = 128;
+template <int RM>
+__global__ void __launch_bounds__(DISNEY_TPB, 6) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
   if (i >= count) return;
-  ShadeIn s = loadShadeIn(c, c.pb.qMat[Q_DISNEY][i], depth);
+  ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DISNEY][i], depth);
   Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, true);
   const DisneyParams dp = s.m->dis;
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
   float3 baseColor = f3(dp.color);
+  const DisneyHit dh(dp, baseColor, N);
   float3 Tprev = mk3(c.pb.thr[s.path]);
   float3 L, H;
   const int nL = c.scene.nLights;
@@ -291,9 +302,9 @@ __global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t coun
       shadowCount++;
       H = normalize(L + V);
       float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
-      float objPdf = disneyPdf(dp, N, L, H);
+      float objPdf = dh.pdf(L, H);
       if (lightPdf > 0 && objPdf > 0) {
-        float3 brdf = disneyEval(dp, baseColor, N, L, V, H);
+        float3 brdf = dh.eval(L, V, H);
         contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
       }
     }
@@ -318,9 +329,9 @@ __global__ void __launch_bounds__(TPB) k_shade_disney(LaunchCtx c, uint32_t coun
   }
   disneySample(s.rng, dp, N, L, V, H);
   if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
-    float pdf = disneyPdf(dp, N, L, H);
+    float pdf = dh.pdf(L, H);
     if (pdf > 0) {
-      float3 brdf = disneyEval(dp, baseColor, N, L, V, H);
+      float3 brdf = dh.eval(L, V, H);
       spawn(c, s.path, a.front, L, brdf / pdf, s.rng.forkState((int)depth + 1));
     }
   }
@@ -396,7 +407,9 @@ inline unsigned grid(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
 void launchGenerate(const LaunchCtx& c, uint32_t nSamples) {
   uint32_t n = nSamples * c.nOwned;
-  if (n) k_generate<<<grid(n), TPB, 0, c.stream>>>(c, n);
+  if (!n) return;
+  if (c.rp.rngMode == 0) k_generate<0><<<grid(n), TPB, 0, c.stream>>>(c, n);
+  else k_generate<1><<<grid(n), TPB, 0, c.stream>>>(c, n);
 }
 template <bool ANYHIT, bool COUNT>
 static unsigned persistentGrid(uint32_t count) {
@@ -445,11 +458,24 @@ void launchLogic(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint
 }
 void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
   if (!count) return;
+  const bool ref = c.rp.rngMode == 0;
   switch (kind) {
-    case Q_LAMBERT: k_shade_diffuse<false><<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
-    case Q_METAL: k_shade_diffuse<true><<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
-    case Q_DIELECTRIC: k_shade_dielectric<<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
-    case Q_DISNEY: k_shade_disney<<<grid(count), TPB, 0, c.stream>>>(c, count, depth); break;
+    case Q_LAMBERT:
+      if (ref) k_shade_diffuse<false, 0><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
+      else k_shade_diffuse<false, 1><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
+      break;
+    case Q_METAL:
+      if (ref) k_shade_diffuse<true, 0><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
+      else k_shade_diffuse<true, 1><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
+      break;
+    case Q_DIELECTRIC:
+      if (ref) k_shade_dielectric<0><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
+      else k_shade_dielectric<1><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
+      break;
+    case Q_DISNEY:
+      if (ref) k_shade_disney<0><<<(count + DISNEY_TPB - 1) / DISNEY_TPB, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
+      else k_shade_disney<1><<<(count + DISNEY_TPB - 1) / DISNEY_TPB, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
+      break;
   }
 }
 void launchShadow(const LaunchCtx& c, uint32_t disneyCount) {
