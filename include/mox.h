@@ -165,6 +165,11 @@ int mox_render(mox_ctx*, uint32_t spp, uint32_t seed);
 /* accuBuffer map()/unmap() (MinimalOptiX.cpp:44,60): W*H*3 floats, row 0 =
  * bottom of the image, un-normalised sums.  Pixels of other ranks are 0. */
 int mox_read_accum(mox_ctx*, float* dst_rgb);
+/* The map()/unmap() form itself: *out points at a pinned host copy of the accumulation buffer
+ * (W*H*3 floats, valid until the next mox_map_accum / mox_read_accum / mox_destroy); no second
+ * host copy is made.  mox_unmap_accum is a no-op kept for symmetry with the reference. */
+int mox_map_accum(mox_ctx*, const float** out);
+int mox_unmap_accum(mox_ctx*);
 int mox_clear_accum(mox_ctx*);
 
 /* Multi-GPU gather plumbing (device pointers on this context's GPU).

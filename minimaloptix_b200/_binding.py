@@ -38,6 +38,8 @@ SIGNATURES = {
     "launch": (C.c_int, [_vp, _i32]),
     "render": (C.c_int, [_vp, _u32, _u32]),
     "read_accum": (C.c_int, [_vp, _vp]),
+    "map_accum": (C.c_int, [_vp, C.POINTER(_fp)]),
+    "unmap_accum": (C.c_int, [_vp]),
     "clear_accum": (C.c_int, [_vp]),
     "owned_pixels": (C.c_int, [_vp, _u32, C.POINTER(_u64)]),
     "pack_owned": (C.c_int, [_vp, _vp]),
@@ -188,6 +190,12 @@ class Context:
         out = np.empty((self.height, self.width, 3), dtype=np.float32)
         self._ck(self.b.read_accum(self.h, _ptr(out)), "read_accum")
         return out
+
+    def map_accum(self):
+        """Zero-copy view (H, W, 3) of the pinned host copy; valid until the next map/read."""
+        p = _fp()
+        self._ck(self.b.map_accum(self.h, C.byref(p)), "map_accum")
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))
 
     def clear_accum(self):
         self._ck(self.b.clear_accum(self.h), "clear_accum")

@@ -605,6 +605,21 @@ int mox_read_accum(mox_ctx* c, float* dst) {
   return MOX_OK;
 }
 
+int mox_map_accum(mox_ctx* c, const float** out) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!out || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
+  int rc = bind(c);
+  if (rc) return rc;
+  size_t bytes = (size_t)c->accuW * c->accuH * 12;
+  if ((rc = ensurePinned(c, bytes))) return rc;
+  CUCK(c, cudaMemcpyAsync(c->pinned, c->dAccu, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  *out = c->pinned;
+  return MOX_OK;
+}
+
+int mox_unmap_accum(mox_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
+
 int mox_clear_accum(mox_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
   int rc = bind(c);

@@ -767,6 +767,8 @@ int orc_read_accum(orc_ctx* c, float* dst) {
   std::copy(c->accu.begin(), c->accu.end(), dst);
   return MOX_OK;
 }
+int orc_map_accum(orc_ctx* c, const float** out) { if (!c || !out) return MOX_ERR_INVALID; *out = c->accu.data(); return MOX_OK; }
+int orc_unmap_accum(orc_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
 int orc_clear_accum(orc_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
   std::fill(c->accu.begin(), c->accu.end(), 0.f);

@@ -32,6 +32,8 @@ int orc_build_accel(orc_ctx*, uint32_t flags, float* out_build_ms);
 int orc_launch(orc_ctx*, int32_t randSeed);
 int orc_render(orc_ctx*, uint32_t spp, uint32_t seed);
 int orc_read_accum(orc_ctx*, float* dst_rgb);
+int orc_map_accum(orc_ctx*, const float** out);
+int orc_unmap_accum(orc_ctx*);
 int orc_clear_accum(orc_ctx*);
 int orc_owned_pixels(orc_ctx*, uint32_t rank, uint64_t* out_n);
 int orc_pack_owned(orc_ctx*, void* dst);            /* host pointers in the oracle */

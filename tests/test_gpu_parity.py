@@ -239,6 +239,7 @@ def test_batched_render_equals_single_launches(host, api_tables, gpu_backend):
     for k in range(6):
         g2.launch(host.launch_seed(k, 123))
     assert np.array_equal(g1.read_accum().view(np.uint32), g2.read_accum().view(np.uint32))
+    assert np.array_equal(g1.map_accum(), g1.read_accum())  # map() view == copied read
     # progressive: two renders continue the seed schedule
     g2.clear_accum()
     g2.render(2, 123)
