@@ -12,7 +12,7 @@ CSRC := $(PKG)/csrc
 REF ?= /root/reference/MinimalOptiX
 
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC,-Wall \
-           -Iinclude -I$(CSRC) -I$(CSRC)/gpu --expt-relaxed-constexpr
+           -Iinclude -I$(CSRC) -I$(CSRC)/gpu --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wno-unused-function -Iinclude -I$(CSRC)
 # The oracle must round every product and sum separately (no FMA contraction).
 ORCFLAGS := -O2 -std=c++17 -fPIC -Wall -ffp-contract=off -fno-fast-math -pthread -Iinclude

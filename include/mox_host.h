@@ -73,6 +73,13 @@ int moxh_write_image(const char* path, const uint8_t* rgb, uint32_t width, uint3
 int moxh_write_accum(const char* path, const float* accum, uint32_t width, uint32_t height, uint64_t launches);
 int moxh_read_accum(const char* path, float* accum, uint32_t width, uint32_t height, uint64_t* launches);
 
+/* Texture image decoding as the loader does it (PNG 8-bit non-interlaced, binary PPM/PGM, PFM):
+ * RGBA float texels, row 0 = bottom, alpha 1 (QImage::pixelColor -> redF(), MinimalOptiX.cpp:459-470).
+ * *texels is malloc()ed; release with moxh_free. */
+int moxh_read_image(const char* path, int* w, int* h, float** texels);
+void moxh_free(void*);
+uint32_t moxh_scene_texture_count(const moxh_scene*);
+
 /* The OBJ reader on its own (loader parity tests). */
 int moxh_obj_parse_double(const char* text, double* out);
 

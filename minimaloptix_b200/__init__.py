@@ -11,7 +11,7 @@ from . import structs
 from ._binding import Backend, Context, MoxError, GPU_ONLY
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GPU_LIB = os.path.join(_HERE, "libmox.so")
+GPU_LIB = os.environ.get("MOX_GPU_LIB") or os.path.join(_HERE, "libmox.so")  # override: A/B testing of builds
 
 _gpu = None
 

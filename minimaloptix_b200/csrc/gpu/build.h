@@ -30,7 +30,7 @@ struct PlocScratch {
 bool plocAlloc(PlocScratch& s, int n, std::string& err);
 void plocFree(PlocScratch& s);
 bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* primLo, const float4* primHi, int radius,
-               BvhNode2* outNodes, float rootLo[3], float rootHi[3], cudaStream_t stream, std::string& err);
+               BvhNode2* outNodes, float rootLo[3], float rootHi[3], int* maxDepthOut, cudaStream_t stream, std::string& err);
 
 struct BuildOutput {
   BvhNode2* nodes = nullptr;  // device, owned by the caller after a successful build
@@ -38,6 +38,8 @@ struct BuildOutput {
   float4* packed = nullptr;   // device, 3 float4 per valid primitive in leaf order
   int nValid = 0, nInvalid = 0;
   int iterations = 0;
+  bool usedPloc = false;  // false: Karras radix tree (requested, or PLOC fallback because of depth)
+  int maxDepth = 0;   // deepest leaf (PLOC); the traversal stack holds MOX_STACK entries
   float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0};
   float4 *scratchLo = nullptr, *scratchHi = nullptr;  // builder-internal
 };

@@ -479,13 +479,18 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out.nNodes = nInner;
   if (in.usePloc) {
     std::string perr;
-    if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, stream, perr)) return bail(perr);
+    if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
+    if (out.maxDepth <= MOX_TRAVERSAL_STACK - 2) {
     k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, out.packed);
     if (in.evStop) CKB(cudaEventRecord(in.evStop, stream));
     CKB(cudaStreamSynchronize(stream));
     CKB(cudaGetLastError());
+    out.usedPloc = true;
     freeScratch();
     return true;
+    }
+    // too deep for the traversal stack: fall through to the radix tree (depth <= 62)
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, out.packed);
   }
   k_karras<<<divUp(nInner, B), B, 0, stream>>>(nValid, kin, children, range, parentInternal, parentLeaf);
   k_refit<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, boxLo, boxHi, children, parentInternal, parentLeaf, nodeLo, nodeHi, arrivals);

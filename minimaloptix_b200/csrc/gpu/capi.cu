@@ -65,11 +65,17 @@ struct mox_ctx {
   std::vector<Analytic> analytic;
   std::vector<GpuMaterial> mats;
   std::vector<LightParams> lights;
+  struct HostTexture { int w, h; std::vector<float> texels; };
+  std::vector<HostTexture> textures;
+  std::vector<cudaArray_t> texArrays;
+  std::vector<cudaTextureObject_t> texObjects;
+  bool texturesDirty = false;
   uint32_t nSpheres = 0, nQuads = 0;
 
   // device scene
   DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights;
   DevBuf dQueryO, dQueryD, dQueryCounters;  // raw ray queries
+  DevBuf dTexObjs;
   BvhNode2* dNodes = nullptr;
   float4* dPacked = nullptr;
   int nNodes = 0, nValid = 0;
@@ -226,9 +232,48 @@ SceneView sceneView(const mox_ctx* c) {
   s.uvs = (const float*)c->dUvs.p;
   s.tris = (const TriIdx*)c->dTris.p;
   s.lights = (const LightParams*)c->dLights.p;
+  s.textures = (const cudaTextureObject_t*)c->dTexObjs.p;
   s.nLights = (int)c->lights.size();
   s.nPrims = (int)c->prims.size();
   return s;
+}
+
+void freeTextures(mox_ctx* c) {
+  for (auto t : c->texObjects) cudaDestroyTextureObject(t);
+  for (auto a : c->texArrays) cudaFreeArray(a);
+  c->texObjects.clear(); c->texArrays.clear();
+}
+
+// createTextureSampler: REPEAT wrap, LINEAR filter, normalized coordinates, float4 texels
+// (MinimalOptiX.cpp:449-474) -> CUDA texture objects; the hardware filter is used as in OptiX.
+int syncTextures(mox_ctx* c) {
+  if (!c->texturesDirty) return MOX_OK;
+  cudaStreamSynchronize(c->stream);
+  freeTextures(c);
+  for (auto& t : c->textures) {
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float4>();
+    cudaArray_t arr = nullptr;
+    CUCK(c, cudaMallocArray(&arr, &fmt, t.w, t.h));
+    c->texArrays.push_back(arr);
+    CUCK(c, cudaMemcpy2DToArray(arr, 0, 0, t.texels.data(), (size_t)t.w * 16, (size_t)t.w * 16, t.h, cudaMemcpyHostToDevice));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof res);
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t obj = 0;
+    CUCK(c, cudaCreateTextureObject(&obj, &res, &td, nullptr));
+    c->texObjects.push_back(obj);
+  }
+  int rc = upload(c, c->dTexObjs, c->texObjects);
+  if (rc) return rc;
+  c->texturesDirty = false;
+  return MOX_OK;
 }
 
 int syncLights(mox_ctx* c) {
@@ -324,6 +369,7 @@ int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
   if (rc) return rc;
   if ((rc = refreshOwned(c))) return rc;
   if ((rc = syncLights(c))) return rc;
+  if ((rc = syncTextures(c))) return rc;
   if (c->nOwned == 0) { c->launches += seeds.size(); return MOX_OK; }
   size_t perBatch = std::max<size_t>(1, c->maxBatchPaths / c->nOwned);
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
@@ -393,6 +439,8 @@ void mox_destroy(mox_ctx* c) {
   for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dQueryO,
                    &c->dQueryD, &c->dQueryCounters}) b->release();
   for (auto& b : c->otherOwned) b.release();
+  freeTextures(c);
+  c->dTexObjs.release();
   cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dAccu); cudaFree(c->dOwned);
   freePaths(c->pb);
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -451,9 +499,16 @@ int mox_set_partition(mox_ctx* c, uint32_t rank, uint32_t world, uint32_t tile) 
   return MOX_OK;
 }
 
-int mox_add_texture_rgba32f(mox_ctx* c, const float*, int, int, int*) {
+int mox_add_texture_rgba32f(mox_ctx* c, const float* texels, int w, int h, int* out_id) {
   if (!c) return MOX_ERR_INVALID;
-  return fail(c, MOX_ERR_INVALID, "textures are not built yet (SURVEY.md §8 f-1)");
+  if (!texels || w <= 0 || h <= 0 || w > 32768 || h > 32768) return fail(c, MOX_ERR_INVALID, "bad texture");
+  mox_ctx::HostTexture t;
+  t.w = w; t.h = h;
+  t.texels.assign(texels, texels + (size_t)w * h * 4);
+  c->textures.push_back(std::move(t));
+  c->texturesDirty = true;
+  if (out_id) *out_id = (int)c->textures.size();
+  return MOX_OK;
 }
 
 int mox_add_sphere(mox_ctx* c, const SphereParams* s, int kind, const void* params, uint32_t* out_id) {
@@ -536,6 +591,7 @@ int mox_clear_scene(mox_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
   c->prims.clear(); c->tris.clear(); c->verts.clear(); c->normals.clear(); c->uvs.clear(); c->analytic.clear();
   c->mats.clear(); c->lights.clear();
+  c->textures.clear(); c->texturesDirty = true;
   c->nSpheres = c->nQuads = 0;
   c->built = false; c->lightsDirty = true;
   return MOX_OK;
@@ -554,6 +610,10 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   if ((rc = upload(c, c->dAnalytic, c->analytic))) return rc;
   if ((rc = upload(c, c->dMats, c->mats))) return rc;
   if ((rc = syncLights(c))) return rc;
+  if ((rc = syncTextures(c))) return rc;
+  for (auto& m : c->mats)
+    if (m.kind == MOX_MAT_DISNEY && (m.dis.albedoID < 0 || m.dis.albedoID > (int)c->textures.size()))
+      return fail(c, MOX_ERR_INVALID, "DisneyParams.albedoID refers to a texture that was not added");
   cudaFree(c->dNodes); cudaFree(c->dPacked);
   c->dNodes = nullptr; c->dPacked = nullptr;
   BuildInput in;

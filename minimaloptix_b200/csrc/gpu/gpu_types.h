@@ -40,6 +40,12 @@ static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 #define MOX_EMPTY_CHILD ((int)0x80000000)
 #define MOX_FAR 3.0e38f   // box coordinates of an empty child: every slab test misses it
 #define MOX_LEAF_MAX 4
+// Per-lane traversal stack entries (far children only): a tree of depth d needs at most d.
+// The Karras radix tree is at most 62 deep (30 key bits + 32 index tie-break bits); PLOC trees
+// are usually ~2 log2(n) deep but can degenerate on scenes with very uneven primitive sizes
+// (measured: 103 levels on the coffee scene), so the builder checks the depth and falls back to
+// the radix tree when a PLOC tree would not fit.
+#define MOX_TRAVERSAL_STACK 128
 
 // Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.
 //   triangle: (p0, idbits) (e0 = p1 - p0, -) (e1 = p0 - p2, -)
@@ -58,6 +64,7 @@ struct SceneView {
   const float* uvs;      // uv
   const TriIdx* tris;
   const LightParams* lights;
+  const cudaTextureObject_t* textures;  // id - 1 -> float4 texture, bilinear, REPEAT, normalized coords
   int nLights;
   int nPrims;
 };

@@ -177,25 +177,32 @@ k_ploc_merge(int n, int nLeaves, uint32_t nodeBase, const uint32_t* __restrict__
 // Position of the leftmost leaf of `node` in depth-first (leaf) order: walking up, every time we
 // are a right child the left sibling's whole subtree precedes us.
 __device__ __forceinline__ uint32_t leftmostPos(uint32_t node, uint32_t root, int nLeaves, const uint32_t* __restrict__ parent,
-                                                const uint2* __restrict__ children, const uint32_t* __restrict__ size) {
-  uint32_t pos = 0;
+                                                const uint2* __restrict__ children, const uint32_t* __restrict__ size,
+                                                uint32_t* depthOut = nullptr) {
+  uint32_t pos = 0, depth = 0;
   while (node != root) {
     uint32_t p = parent[node];
     uint2 ch = children[p - nLeaves];
     if (ch.y == node) pos += size[ch.x];
     node = p;
+    ++depth;
   }
+  if (depthOut) *depthOut = depth;
   return pos;
 }
 
 __global__ void k_ploc_leaf_order(int nLeaves, uint32_t root, const uint32_t* __restrict__ parent, const uint2* __restrict__ children,
                                   const uint32_t* __restrict__ size, const uint32_t* __restrict__ sortedIds,
-                                  uint32_t* __restrict__ leafPos, uint32_t* __restrict__ orderedIds) {
+                                  uint32_t* __restrict__ leafPos, uint32_t* __restrict__ orderedIds, uint32_t* __restrict__ maxDepth) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nLeaves) return;
-  uint32_t pos = leftmostPos((uint32_t)i, root, nLeaves, parent, children, size);
-  leafPos[i] = pos;
-  orderedIds[pos] = sortedIds[i];
+  uint32_t depth = 0;
+  if (i < nLeaves) {
+    uint32_t pos = leftmostPos((uint32_t)i, root, nLeaves, parent, children, size, &depth);
+    leafPos[i] = pos;
+    orderedIds[pos] = sortedIds[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, o));
+  if ((threadIdx.x & 31) == 0 && depth) atomicMax(maxDepth, depth);
 }
 
 // Aila–Laine nodes; inner node k (creation order) is written at nInner-1-k so the root is node 0
@@ -249,7 +256,7 @@ bool plocAlloc(PlocScratch& s, int n, std::string& err) {
   PCK(cudaMalloc(&s.children, nn * 8));
   PCK(cudaMalloc(&s.parent, 2 * nn * 4)); PCK(cudaMalloc(&s.size, 2 * nn * 4));
   PCK(cudaMalloc(&s.leafPos, nn * 4)); PCK(cudaMalloc(&s.orderedIds, nn * 4));
-  PCK(cudaMalloc(&s.tileSums, (size_t)(divUp(nn, PL_TILE) + 1) * 8));
+  PCK(cudaMalloc(&s.tileSums, (size_t)(divUp(nn, PL_TILE) + 2) * 8));
   PCK(cudaMallocHost(&s.hostTotal, 8));
   return true;
 }
@@ -265,7 +272,7 @@ void plocFree(PlocScratch& s) {
 // n >= 2 valid primitives in Morton order (sortedIds); primLo/primHi indexed by primitive id.
 // Writes n-1 nodes to outNodes (root = node 0) and the leaf-ordered ids to s.orderedIds.
 bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* primLo, const float4* primHi, int radius,
-               BvhNode2* outNodes, float rootLo[3], float rootHi[3], cudaStream_t stream, std::string& err) {
+               BvhNode2* outNodes, float rootLo[3], float rootHi[3], int* maxDepthOut, cudaStream_t stream, std::string& err) {
   radius = std::max(1, std::min(radius, PL_MAX_RADIUS));
   const int B = 256;
   k_ploc_init<<<divUp(n, B), B, 0, stream>>>(n, sortedIds, primLo, primHi, s.cid[0], s.cLo[0], s.cHi[0], s.nodeLo, s.nodeHi, s.size);
@@ -294,13 +301,18 @@ bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* p
   const int nInner = n - 1;
   if ((int)nodeBase != nInner) { err = "PLOC node count mismatch"; return false; }
   const uint32_t root = (uint32_t)(n + nInner - 1);
-  k_ploc_leaf_order<<<divUp(n, B), B, 0, stream>>>(n, root, s.parent, s.children, s.size, sortedIds, s.leafPos, s.orderedIds);
+  uint32_t* dDepth = (uint32_t*)(dTotal + 1);
+  PCK(cudaMemsetAsync(dDepth, 0, 4, stream));
+  k_ploc_leaf_order<<<divUp(n, B), B, 0, stream>>>(n, root, s.parent, s.children, s.size, sortedIds, s.leafPos, s.orderedIds, dDepth);
   k_ploc_emit<<<divUp(nInner, B), B, 0, stream>>>(n, nInner, root, s.parent, s.children, s.size, s.leafPos, s.nodeLo, s.nodeHi, outNodes);
   float4 lo, hi;
   PCK(cudaMemcpyAsync(&lo, s.nodeLo + root, 16, cudaMemcpyDeviceToHost, stream));
   PCK(cudaMemcpyAsync(&hi, s.nodeHi + root, 16, cudaMemcpyDeviceToHost, stream));
+  uint32_t depth = 0;
+  PCK(cudaMemcpyAsync(&depth, dDepth, 4, cudaMemcpyDeviceToHost, stream));
   PCK(cudaStreamSynchronize(stream));
   PCK(cudaGetLastError());
+  *maxDepthOut = (int)depth;
   rootLo[0] = lo.x; rootLo[1] = lo.y; rootLo[2] = lo.z;
   rootHi[0] = hi.x; rootHi[1] = hi.y; rootHi[2] = hi.z;
   return true;

@@ -74,7 +74,7 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
   return tn <= tf ? tn : __int_as_float(0x7f800000);
 }
 
-#define MOX_STACK 64
+#define MOX_STACK MOX_TRAVERSAL_STACK
 #define MOX_DONE ((int)0x80000000)   // sentinel "no more nodes" (same bit pattern as an empty child)
 #define MOX_FETCH_THRESHOLD 20       // refill a warp's idle lanes when fewer than this many are traversing
 

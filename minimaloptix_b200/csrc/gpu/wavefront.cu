@@ -79,9 +79,12 @@ __global__ void __launch_bounds__(TPB) k_generate(LaunchCtx c, uint32_t nPaths) 
 
 // ------------------------------------------------------------------ traversal + classify
 constexpr int TRAV_TPB = 128;
+#ifndef MOX_TRAV_MINBLOCKS
+#define MOX_TRAV_MINBLOCKS 1
+#endif
 
 template <bool ANYHIT, bool COUNT>
-__global__ void __launch_bounds__(TRAV_TPB) k_traverse(SceneView s, TraceJob job) {
+__global__ void __launch_bounds__(TRAV_TPB, MOX_TRAV_MINBLOCKS) k_traverse(SceneView s, TraceJob job) {
   traverseWarpPersistent<ANYHIT, COUNT>(s, job);
 }
 
@@ -177,6 +180,13 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
   return a;
 }
 
+// Material.cu:126-132: constant colour, or rtTex2D<float4>(albedoID, u, v).rgb
+__device__ __forceinline__ float3 disneyBaseColor(const SceneView& s, const DisneyParams& dp, float u, float v) {
+  if (dp.albedoID == MOX_TEXTURE_ID_NULL) return f3(dp.color);
+  float4 t = tex2D<float4>(s.textures[dp.albedoID - 1], u, v);
+  return mk3(t.x, t.y, t.z);
+}
+
 template <int RM>
 struct ShadeIn {
   uint32_t path;
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(TPB) k_shade_dielectric(LaunchCtx c, uint32_t 
   float ior;
   float3 tint;
   if (s.m->kind == MOX_MAT_GLASS) { ior = s.m->gls.refIdx; tint = f3(s.m->gls.albedo); }
-  else { ior = 1.45f; tint = f3(s.m->dis.color); }
+  else { ior = 1.45f; tint = disneyBaseColor(c.scene, s.m->dis, a.u, a.v); }
   float3 normal = a.Ns;
   float cosI = -dot(s.d, normal);
   float refIdx;
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, 6) k_shade_disney(LaunchCtx c, uin
   const DisneyParams dp = s.m->dis;
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
-  float3 baseColor = f3(dp.color);
+  float3 baseColor = disneyBaseColor(c.scene, dp, a.u, a.v);
   const DisneyHit dh(dp, baseColor, N);
   float3 Tprev = mk3(c.pb.thr[s.path]);
   float3 L, H;

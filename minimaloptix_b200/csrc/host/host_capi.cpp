@@ -1,4 +1,5 @@
 // host_capi.cpp — extern "C" surface of libmox_host.so (include/mox_host.h).
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -155,6 +156,19 @@ int moxh_read_accum(const char* path, float* accum, uint32_t w, uint32_t h, uint
   std::string err;
   return readAccum(path, accum, w, h, launches, err) ? 0 : fail(err);
 }
+int moxh_read_image(const char* path, int* w, int* h, float** texels) {
+  if (!path || !w || !h || !texels) return fail("bad argument");
+  std::vector<float> t;
+  std::string err;
+  if (!readImageRgba(path, *w, *h, t, err)) return fail(err);
+  *texels = (float*)malloc(t.size() * sizeof(float));
+  if (!*texels) return fail("out of memory");
+  memcpy(*texels, t.data(), t.size() * sizeof(float));
+  return 0;
+}
+void moxh_free(void* p) { free(p); }
+uint32_t moxh_scene_texture_count(const moxh_scene* s) { return s ? (uint32_t)s->d.textures.size() : 0; }
+
 int moxh_obj_parse_double(const char* text, double* out) {
   return tinyobj::tryParseDouble(text, text + strlen(text), out) ? 1 : 0;
 }

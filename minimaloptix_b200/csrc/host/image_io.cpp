@@ -3,7 +3,9 @@
 // QImage/QColor replaced by a dependency-free PNG/PPM writer).
 #include "image_io.h"
 
+#include <cctype>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -96,6 +98,244 @@ bool writeImage(const std::string& path, const uint8_t* rgb, uint32_t W, uint32_
   chunk(f, "IEND", {});
   fclose(f);
   return true;
+}
+
+// ------------------------------------------------------------------ image decoding (textures)
+namespace {
+
+// RFC 1951 inflate: stored, fixed and dynamic Huffman blocks.
+struct Inflater {
+  const uint8_t* in; size_t n, pos = 0; uint32_t bitBuf = 0; int bitCnt = 0;
+  std::vector<uint8_t>& out;
+  bool ok = true;
+  Inflater(const uint8_t* p, size_t len, std::vector<uint8_t>& o) : in(p), n(len), out(o) {}
+  uint32_t bits(int need) {
+    while (bitCnt < need) {
+      if (pos >= n) { ok = false; return 0; }
+      bitBuf |= (uint32_t)in[pos++] << bitCnt;
+      bitCnt += 8;
+    }
+    uint32_t v = bitBuf & ((need == 32) ? 0xffffffffu : ((1u << need) - 1u));
+    bitBuf >>= need; bitCnt -= need;
+    return v;
+  }
+  struct Huff { uint16_t count[16]; uint16_t symbol[288]; };
+  static void build(Huff& h, const uint8_t* len, int nsym) {
+    memset(h.count, 0, sizeof h.count);
+    for (int i = 0; i < nsym; ++i) h.count[len[i]]++;
+    h.count[0] = 0;
+    uint16_t offs[16]; offs[1] = 0;
+    for (int i = 1; i < 15; ++i) offs[i + 1] = offs[i] + h.count[i];
+    for (int i = 0; i < nsym; ++i) if (len[i]) h.symbol[offs[len[i]]++] = (uint16_t)i;
+  }
+  int decode(const Huff& h) {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; ++len) {
+      code |= (int)bits(1);
+      if (!ok) return -1;
+      int count = h.count[len];
+      if (code - count < first) return h.symbol[index + (code - first)];
+      index += count; first += count; first <<= 1; code <<= 1;
+    }
+    ok = false;
+    return -1;
+  }
+  bool codes(const Huff& lit, const Huff& dist) {
+    static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint16_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint16_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (;;) {
+      int sym = decode(lit);
+      if (!ok) return false;
+      if (sym < 256) out.push_back((uint8_t)sym);
+      else if (sym == 256) return true;
+      else {
+        sym -= 257;
+        if (sym >= 29) return false;
+        int len = lbase[sym] + (int)bits(lext[sym]);
+        int ds = decode(dist);
+        if (!ok || ds < 0 || ds >= 30) return false;
+        size_t d = dbase[ds] + bits(dext[ds]);
+        if (!ok || d > out.size()) return false;
+        size_t from = out.size() - d;
+        for (int k = 0; k < len; ++k) out.push_back(out[from + k]);
+      }
+    }
+  }
+  bool run() {
+    for (;;) {
+      uint32_t last = bits(1), type = bits(2);
+      if (!ok) return false;
+      if (type == 0) {
+        bitBuf = 0; bitCnt = 0;
+        if (pos + 4 > n) return false;
+        uint32_t len = in[pos] | (in[pos + 1] << 8);
+        pos += 4;
+        if (pos + len > n) return false;
+        out.insert(out.end(), in + pos, in + pos + len);
+        pos += len;
+      } else if (type == 1) {
+        uint8_t l[288];
+        for (int i = 0; i < 144; ++i) l[i] = 8;
+        for (int i = 144; i < 256; ++i) l[i] = 9;
+        for (int i = 256; i < 280; ++i) l[i] = 7;
+        for (int i = 280; i < 288; ++i) l[i] = 8;
+        Huff lit, dist;
+        build(lit, l, 288);
+        uint8_t dl[30];
+        for (int i = 0; i < 30; ++i) dl[i] = 5;
+        build(dist, dl, 30);
+        if (!codes(lit, dist)) return false;
+      } else if (type == 2) {
+        int nlen = (int)bits(5) + 257, ndist = (int)bits(5) + 1, ncode = (int)bits(4) + 4;
+        if (!ok || nlen > 286 || ndist > 30) return false;
+        static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        uint8_t lengths[320];
+        memset(lengths, 0, sizeof lengths);
+        for (int i = 0; i < ncode; ++i) lengths[order[i]] = (uint8_t)bits(3);
+        Huff lencode;
+        build(lencode, lengths, 19);
+        uint8_t ll[320];
+        memset(ll, 0, sizeof ll);
+        int idx = 0;
+        while (idx < nlen + ndist) {
+          int sym = decode(lencode);
+          if (!ok) return false;
+          if (sym < 16) ll[idx++] = (uint8_t)sym;
+          else {
+            int rep, val = 0;
+            if (sym == 16) { if (idx == 0) return false; val = ll[idx - 1]; rep = 3 + (int)bits(2); }
+            else if (sym == 17) rep = 3 + (int)bits(3);
+            else rep = 11 + (int)bits(7);
+            if (idx + rep > nlen + ndist) return false;
+            while (rep--) ll[idx++] = (uint8_t)val;
+          }
+        }
+        Huff lit, dist;
+        build(lit, ll, nlen);
+        build(dist, ll + nlen, ndist);
+        if (!codes(lit, dist)) return false;
+      } else {
+        return false;
+      }
+      if (last) return ok;
+    }
+  }
+};
+
+bool readWhole(const std::string& path, std::vector<uint8_t>& data) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  uint8_t buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + n);
+  fclose(f);
+  return true;
+}
+
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+// rows top-down, `ch` channels of 8 bit -> RGBA float, flipped so row 0 is the bottom
+void toTexels(const std::vector<uint8_t>& px, int w, int h, int ch, const uint8_t* palette, std::vector<float>& texels) {
+  texels.resize((size_t)w * h * 4);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const uint8_t* s = &px[((size_t)y * w + x) * ch];
+      float r, g, b;
+      if (palette) { const uint8_t* q = palette + 3 * s[0]; r = q[0]; g = q[1]; b = q[2]; }
+      else if (ch <= 2) { r = g = b = s[0]; }
+      else { r = s[0]; g = s[1]; b = s[2]; }
+      float* d = &texels[((size_t)(h - 1 - y) * w + x) * 4];
+      d[0] = r / 255.0f; d[1] = g / 255.0f; d[2] = b / 255.0f; d[3] = 1.f;  // QColor::redF() == value / 255
+    }
+}
+
+bool readPng(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& texels, std::string& err) {
+  size_t pos = 8;
+  int depth = 0, ctype = 0, interlace = 0;
+  std::vector<uint8_t> idat, palette;
+  while (pos + 12 <= f.size()) {
+    uint32_t len = be32(&f[pos]);
+    const uint8_t* type = &f[pos + 4];
+    if (pos + 12 + len > f.size()) break;
+    const uint8_t* body = &f[pos + 8];
+    if (!memcmp(type, "IHDR", 4) && len >= 13) { w = (int)be32(body); h = (int)be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12]; }
+    else if (!memcmp(type, "PLTE", 4)) palette.assign(body, body + len);
+    else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+    else if (!memcmp(type, "IEND", 4)) break;
+    pos += 12 + len;
+  }
+  if (w <= 0 || h <= 0 || depth != 8 || interlace != 0) { err = "unsupported PNG (need 8-bit, non-interlaced)"; return false; }
+  int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  if (!ch || (ctype == 3 && palette.size() < 3) || idat.size() < 6) { err = "unsupported PNG colour type"; return false; }
+  std::vector<uint8_t> raw;
+  raw.reserve((size_t)h * (w * ch + 1));
+  Inflater inf(idat.data() + 2, idat.size() - 2, raw);  // skip the zlib header; the Adler-32 trailer is ignored
+  if (!inf.run() || raw.size() < (size_t)h * ((size_t)w * ch + 1)) { err = "corrupt PNG data"; return false; }
+  const size_t stride = (size_t)w * ch;
+  std::vector<uint8_t> px(stride * h);
+  for (int y = 0; y < h; ++y) {
+    const uint8_t* src = &raw[(size_t)y * (stride + 1)];
+    uint8_t* cur = &px[(size_t)y * stride];
+    const uint8_t* up = y ? cur - stride : nullptr;
+    int ft = src[0];
+    for (size_t i = 0; i < stride; ++i) {
+      int a = i >= (size_t)ch ? cur[i - ch] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)ch) ? up[i - ch] : 0;
+      int v = src[1 + i];
+      switch (ft) {
+        case 1: v += a; break;
+        case 2: v += b; break;
+        case 3: v += (a + b) >> 1; break;
+        case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+        default: break;
+      }
+      cur[i] = (uint8_t)v;
+    }
+  }
+  toTexels(px, w, h, ch, ctype == 3 ? palette.data() : nullptr, texels);
+  return true;
+}
+
+}  // namespace
+
+bool readImageRgba(const std::string& path, int& w, int& h, std::vector<float>& texels, std::string& err) {
+  std::vector<uint8_t> f;
+  if (!readWhole(path, f)) { err = "cannot open " + path; return false; }
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  if (f.size() > 8 && !memcmp(f.data(), sig, 8)) return readPng(f, w, h, texels, err);
+  if (f.size() > 2 && f[0] == 'P' && (f[1] == '6' || f[1] == '5' || f[1] == 'F' || f[1] == 'f')) {
+    // netpbm header: magic, width, height, maxval (or scale for PFM), one whitespace, data
+    size_t pos = 2;
+    double vals[3];
+    for (int k = 0; k < 3; ++k) {
+      while (pos < f.size() && (isspace(f[pos]) || f[pos] == '#')) { if (f[pos] == '#') while (pos < f.size() && f[pos] != '\n') ++pos; else ++pos; }
+      char* end = nullptr;
+      vals[k] = strtod((const char*)&f[pos], &end);
+      pos = (size_t)(end - (const char*)f.data());
+    }
+    ++pos;
+    w = (int)vals[0]; h = (int)vals[1];
+    if (w <= 0 || h <= 0) { err = "bad netpbm header"; return false; }
+    if (f[1] == '6' || f[1] == '5') {
+      int ch = f[1] == '6' ? 3 : 1;
+      if (vals[2] != 255 || pos + (size_t)w * h * ch > f.size()) { err = "unsupported netpbm file"; return false; }
+      std::vector<uint8_t> px(f.begin() + pos, f.begin() + pos + (size_t)w * h * ch);
+      toTexels(px, w, h, ch, nullptr, texels);
+      return true;
+    }
+    int ch = f[1] == 'F' ? 3 : 1;  // PFM: rows bottom-up already, little-endian when scale < 0
+    if (vals[2] >= 0 || pos + (size_t)w * h * ch * 4 > f.size()) { err = "unsupported PFM (need little-endian)"; return false; }
+    texels.resize((size_t)w * h * 4);
+    const float* src = (const float*)&f[pos];
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+      float r = src[i * ch], g = ch == 3 ? src[i * ch + 1] : r, b = ch == 3 ? src[i * ch + 2] : r;
+      texels[4 * i] = r; texels[4 * i + 1] = g; texels[4 * i + 2] = b; texels[4 * i + 3] = 1.f;
+    }
+    return true;
+  }
+  err = "unknown image format: " + path;
+  return false;
 }
 
 bool writeAccum(const std::string& path, const float* accum, uint32_t W, uint32_t H, uint64_t launches, std::string& err) {

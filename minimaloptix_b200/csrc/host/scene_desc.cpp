@@ -6,6 +6,7 @@
 #include <map>
 #include <random>
 
+#include "image_io.h"
 #include "obj_loader.h"
 #include "scene.h"
 #include "utils_host.h"
@@ -186,7 +187,17 @@ bool loadSceneFile(SceneDesc& s, const std::string& sceneDir, const std::string&
       s.warnings.push_back("skipped mesh " + scene.meshNames[i] + ": " + lerr);
       continue;
     }
-    if (!scene.textures[i].empty()) s.warnings.push_back("texture " + scene.textures[i] + " ignored (texture path not built yet)");
+    int texIndex = -1;
+    if (!scene.textures[i].empty()) {  // MinimalOptiX.cpp:445-479, cached by file name
+      for (size_t t = 0; t < s.textures.size(); ++t) if (s.textures[t].name == scene.textures[i]) texIndex = (int)t;
+      if (texIndex < 0) {
+        TextureDesc td;
+        td.name = scene.textures[i];
+        std::string terr;
+        if (readImageRgba(folder + td.name, td.w, td.h, td.texels, terr)) { s.textures.push_back(std::move(td)); texIndex = (int)s.textures.size() - 1; }
+        else s.warnings.push_back("texture " + scene.textures[i] + " not loaded: " + terr);
+      }
+    }
     for (auto& sh : shapes) {
       MeshDesc m;
       m.name = scene.meshNames[i] + ":" + sh.name;
@@ -201,6 +212,7 @@ bool loadSceneFile(SceneDesc& s, const std::string& sceneDir, const std::string&
         m.ti[f] = sh.mesh.indices[f].texcoord_index;
       }
       s.addMesh(std::move(m), disney(scene.materials[i]));
+      s.items.back().texture = texIndex;
     }
   }
   for (auto& light : scene.lights) {  // MinimalOptiX.cpp:495-521
@@ -482,7 +494,12 @@ bool uploadScene(const SceneDesc& s, const MoxApi& api, mox_ctx* ctx, uint32_t w
   if (api.set_globals(ctx, width, height, maxDepth, 0.001f, 0.001f, absorb, bad, s.bg)) return fail("set_globals");
   CamParams cam = s.camParams(width, height);
   if (api.set_camera(ctx, &cam)) return fail("set_camera");
-  for (const Item& it : s.items) {
+  std::vector<int> texIds(s.textures.size(), 0);
+  for (size_t t = 0; t < s.textures.size(); ++t)
+    if (api.add_texture_rgba32f(ctx, s.textures[t].texels.data(), s.textures[t].w, s.textures[t].h, &texIds[t])) return fail("add_texture");
+  for (const Item& itRef : s.items) {
+    Item it = itRef;
+    if (it.texture >= 0 && it.mat.kind == MOX_MAT_DISNEY) it.mat.dis.albedoID = texIds[it.texture];
     int rc = 0;
     if (it.type == Item::SPHERE_ITEM) rc = api.add_sphere(ctx, &it.sphere, it.mat.kind, it.mat.params(), nullptr);
     else if (it.type == Item::QUAD_ITEM) rc = api.add_quad(ctx, &it.quad, it.mat.kind, it.mat.params(), nullptr);

@@ -37,8 +37,11 @@ struct Item {  // one GeometryInstance, in insertion (= primitive id) order
   SphereParams sphere;
   QuadParams quad;
   int mesh = -1;  // index into SceneDesc::meshes
+  int texture = -1;  // index into SceneDesc::textures (Disney albedo), -1 = none
   MaterialBlock mat;
 };
+
+struct TextureDesc { std::string name; int w = 0, h = 0; std::vector<float> texels; };  // RGBA float, row 0 = bottom
 
 struct CameraDesc {
   float3 lookFrom, lookAt, up;
@@ -52,6 +55,7 @@ struct SceneDesc {
   CameraDesc camera;
   std::vector<Item> items;
   std::vector<MeshDesc> meshes;
+  std::vector<TextureDesc> textures;  // Item::texture indexes this; uploaded once each (the reference caches by file name)
   std::vector<LightParams> lights;  // context["lights"] (Disney NEE)
   Aabb aabb;                        // over referenced mesh vertices (MinimalOptiX.cpp:430-433)
   std::vector<std::string> warnings;

@@ -56,6 +56,10 @@ def lib():
         L.moxh_write_accum.argtypes = [C.c_char_p, _vp, _u32, _u32, _u64]
         L.moxh_read_accum.argtypes = [C.c_char_p, _vp, _u32, _u32, C.POINTER(_u64)]
         L.moxh_obj_parse_double.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+        L.moxh_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_float))]
+        L.moxh_free.argtypes = [_vp]
+        L.moxh_scene_texture_count.argtypes = [_vp]
+        L.moxh_scene_texture_count.restype = _u32
         _lib = L
     return _lib
 
@@ -171,10 +175,24 @@ class Scene:
         idx = np.ctypeslib.as_array(vi, shape=(info["faces"], 3)).copy()
         return verts, idx
 
+    def texture_count(self):
+        return lib().moxh_scene_texture_count(self.h)
+
     def upload(self, api_table, ctx, width, height, max_depth):
         if lib().moxh_scene_upload(self.h, api_table.h, ctx.h, width, height, max_depth) != 0:
             raise MoxError("moxh_scene_upload: " + _err())
         ctx.width, ctx.height = width, height
+
+
+def read_image(path):
+    """Decode a texture image the way the loader does: (H, W, 4) float32, row 0 = bottom, alpha 1."""
+    w, h, p = C.c_int(), C.c_int(), C.POINTER(C.c_float)()
+    if lib().moxh_read_image(path.encode(), C.byref(w), C.byref(h), C.byref(p)) != 0:
+        raise MoxError("moxh_read_image: " + _err())
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib().moxh_free(p)
 
 
 def accum_to_rgb8(accum, n_accum):

@@ -201,3 +201,64 @@ def test_builtin_scenes_are_deterministic(host):
 def test_launch_seed_schedule(host, orc):
     assert host.launch_seed(0, 0xC0FFEE) == np.int32(np.uint32(orc.backend().tea16(0, 0xC0FFEE)))
     assert len({host.launch_seed(i, 1) for i in range(64)}) == 64
+
+
+def test_texture_image_decoding(host):
+    """PNG (deflate, all five filter types, RGB / RGBA / gray / palette), PPM and PFM decode to the
+    texels the reference builds from a QImage: value / 255, row 0 = bottom, alpha 1."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, size=(41, 67, 3), dtype=np.uint8)
+    base[:, :, 1] = (np.arange(67)[None, :] * 3 + np.arange(41)[:, None]) % 256  # smooth channel: exercises Sub/Up/Paeth
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("RGB", "RGBA", "L", "P"):
+            img = Image.fromarray(base).convert(mode)
+            p = os.path.join(tmp, f"t_{mode}.png")
+            img.save(p, optimize=True)
+            want = np.asarray(Image.open(p).convert("RGB"), dtype=np.float32) / 255.0
+            got = host.read_image(p)
+            assert got.shape == (41, 67, 4)
+            assert np.array_equal(got[::-1, :, :3], want), mode   # flipped: row 0 is the bottom
+            assert (got[..., 3] == 1).all()
+        p = os.path.join(tmp, "t.ppm")
+        Image.fromarray(base).save(p)
+        assert np.array_equal(host.read_image(p)[::-1, :, :3], base.astype(np.float32) / 255.0)
+        with pytest.raises(Exception):
+            host.read_image(os.path.join(tmp, "missing.png"))
+
+
+def _textured_scene(tmp):
+    """A unit quad mesh with uvs and a 4x4 checker texture, lit by one quad light."""
+    from PIL import Image
+    d = os.path.join(tmp, "tex")
+    os.makedirs(d, exist_ok=True)
+    chk = np.zeros((4, 4, 3), dtype=np.uint8)
+    chk[::2, ::2] = [255, 32, 32]
+    chk[1::2, 1::2] = [32, 255, 32]
+    chk[::2, 1::2] = [32, 32, 255]
+    chk[1::2, ::2] = [240, 240, 240]
+    Image.fromarray(chk).save(os.path.join(d, "checker.png"))
+    with open(os.path.join(d, "floor.obj"), "w") as f:
+        f.write("v -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nvt 0 0\nvt 2 0\nvt 2 2\nvt 0 2\nvn 0 1 0\n"
+                "f 1/1/1 3/3/1 2/2/1\nf 1/1/1 4/4/1 3/3/1\n")
+    with open(os.path.join(d, "tex.scene"), "w") as f:
+        f.write("material Checker\n{\n\tcolor 1 1 1\n\talbedoTex checker.png\n\troughness 0.6\n}\n"
+                "mesh\n{\n\tfile floor.obj\n\tmaterial Checker\n}\n"
+                "light\n{\n\ttype Quad\n\tposition -0.5 2 -0.5\n\tv1 0.5 2 -0.5\n\tv2 -0.5 2 0.5\n\temission 8 8 8\n}\n")
+    return d
+
+
+def test_textured_scene_loads_and_changes_the_oracle_image(host, orc):
+    with tempfile.TemporaryDirectory() as tmp:
+        d = _textured_scene(tmp)
+        sc = host.Scene.load(d, "tex")
+        assert sc.texture_count() == 1 and sc.warnings() == []
+        api = host.ApiTable(orc.ORACLE_LIB, "orc_")
+        ctx = orc.context()
+        sc.upload(api, ctx, 64, 64, 3)
+        ctx.set_camera(host.set_cam_params((0, 1.5, 2.5), (0, 0, 0), (0, 1, 0), 40, 1.0, 0.0, 1.0))
+        ctx.build_accel()
+        ctx.render(8, 3)
+        img = ctx.read_accum() / 8
+        # the checker shows: strongly red and strongly green pixels both exist
+        assert (img[..., 0] > 2 * img[..., 1] + 0.02).any() and (img[..., 1] > 2 * img[..., 0] + 0.02).any()
