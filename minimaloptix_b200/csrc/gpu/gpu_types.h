@@ -39,7 +39,9 @@ struct __align__(16) BvhNode2 { float4 c0xy, c1xy, cz; int4 ref; };
 static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 #define MOX_EMPTY_CHILD ((int)0x80000000)
 #define MOX_FAR 3.0e38f   // box coordinates of an empty child: every slab test misses it
-#define MOX_LEAF_MAX 4
+#ifndef MOX_LEAF_MAX
+#define MOX_LEAF_MAX 2  // measured on the 1M-triangle bench: 2 -> 946, 1 -> 940, 3 -> 935, 4 -> 909, 8 -> 837 Mrays/s
+#endif
 // Per-lane traversal stack entries (far children only): a tree of depth d needs at most d.
 // The Karras radix tree is at most 62 deep (30 key bits + 32 index tie-break bits); PLOC trees
 // are usually ~2 log2(n) deep but can degenerate on scenes with very uneven primitive sizes
