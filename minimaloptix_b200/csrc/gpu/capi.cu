@@ -101,6 +101,8 @@ struct mox_ctx {
   uint64_t extendLaunches = 0, kernelLaunches = 0;
   StageTimer timer;
   size_t maxBatchPaths = 4u << 20;
+  bool sortRays = false;         // reorder the extend queue by (origin cell, direction octant) from bounce 2 on
+  float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {1, 1, 1};
 };
 
 namespace {
@@ -182,7 +184,9 @@ int refreshOwned(mox_ctx* c) {
 
 void freePaths(PathBuffers& pb) {
   cudaFree(pb.rayO); cudaFree(pb.rayD); cudaFree(pb.hit); cudaFree(pb.thr); cudaFree(pb.rad); cudaFree(pb.state);
-  cudaFree(pb.qCur); cudaFree(pb.qNext);
+  for (auto& q : pb.qBuf) cudaFree(q);
+  for (auto& k : pb.kBuf) cudaFree(k);
+  cudaFree(pb.sortScratch);
   for (auto& q : pb.qMat) cudaFree(q);
   cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.shQueue); cudaFree(pb.counters); cudaFree(pb.seeds);
   pb = PathBuffers();
@@ -201,7 +205,9 @@ int ensurePaths(mox_ctx* c, size_t paths, size_t nLights, size_t nSeeds) {
     CUCK(c, cudaMalloc(&pb.rayO, paths * 16)); CUCK(c, cudaMalloc(&pb.rayD, paths * 16));
     CUCK(c, cudaMalloc(&pb.hit, paths * 16)); CUCK(c, cudaMalloc(&pb.thr, paths * 16));
     CUCK(c, cudaMalloc(&pb.rad, paths * 16)); CUCK(c, cudaMalloc(&pb.state, paths * 4));
-    CUCK(c, cudaMalloc(&pb.qCur, paths * 4)); CUCK(c, cudaMalloc(&pb.qNext, paths * 4));
+    for (auto& q : pb.qBuf) CUCK(c, cudaMalloc(&q, paths * 4));
+    for (auto& k : pb.kBuf) CUCK(c, cudaMalloc(&k, paths * 4));
+    CUCK(c, cudaMalloc(&pb.sortScratch, radixSortScratchBytes(paths)));
     for (auto& q : pb.qMat) CUCK(c, cudaMalloc(&q, paths * 4));
     if (slots) {
       CUCK(c, cudaMalloc(&pb.shO, paths * 16)); CUCK(c, cudaMalloc(&pb.shD, slots * 16)); CUCK(c, cudaMalloc(&pb.shC, slots * 16));
@@ -303,6 +309,14 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
   lc.accu = c->dAccu;
   lc.countTraversal = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
   lc.stream = c->stream;
+  lc.sceneLo = make_float3(c->sceneLo[0], c->sceneLo[1], c->sceneLo[2]);
+  {
+    float ex = c->sceneHi[0] - c->sceneLo[0], ey = c->sceneHi[1] - c->sceneLo[1], ez = c->sceneHi[2] - c->sceneLo[2];
+    lc.sceneInvExt = make_float3(ex > 0 ? 128.f / ex : 0.f, ey > 0 ? 128.f / ey : 0.f, ez > 0 ? 128.f / ez : 0.f);
+  }
+  int iCur = 0, iNext = 1, iSpare = 2;
+  lc.pb.qCur = pb.qBuf[iCur]; lc.pb.qNext = pb.qBuf[iNext];
+  lc.pb.qKey = c->sortRays ? pb.kBuf[0] : nullptr;
 
   CUCK(c, cudaMemsetAsync(pb.counters, 0, C_WORDS * 4, c->stream));
   StageTimer& tm = c->timer;
@@ -343,7 +357,17 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     CUCK(c, cudaMemsetAsync(pb.counters, 0, 8 * 4, c->stream));  // next count + material counts
     CUCK(c, cudaStreamSynchronize(c->stream));
     count = host[C_NEXT];
-    std::swap(lc.pb.qCur, lc.pb.qNext);
+    if (c->sortRays && count > 4096) {
+      // 24-bit keys -> 3 passes: the sorted queue lands in (kBuf[1], qBuf[iSpare])
+      tm.begin(ST_SHADE, c->stream);
+      radixSortAsync(pb.kBuf[0], pb.qBuf[iNext], pb.kBuf[1], pb.qBuf[iSpare], (int)count, 3, pb.sortScratch, c->stream);
+      tm.end(c->stream);
+      c->kernelLaunches += 5;
+      int t = iCur; iCur = iSpare; iSpare = iNext; iNext = t;
+    } else {
+      int t = iCur; iCur = iNext; iNext = t;
+    }
+    lc.pb.qCur = pb.qBuf[iCur]; lc.pb.qNext = pb.qBuf[iNext];
   }
   tm.begin(ST_ACCUMULATE, c->stream);
   launchAccumulate(lc, S);
@@ -424,6 +448,7 @@ int mox_create(mox_ctx** out, int device_id) {
     delete c;
     return fail(nullptr, MOX_ERR_CUDA, msg);
   }
+  if (const char* env = getenv("MOX_SORT_RAYS")) c->sortRays = atoi(env) != 0;
   if (const char* env = getenv("MOX_MAX_BATCH_PATHS")) { long long v = atoll(env); if (v > 0) c->maxBatchPaths = (size_t)v; }
   memset(&c->rp, 0, sizeof c->rp);
   c->rp.maxDepth = 256; c->rp.eps = 0.001f; c->rp.minIntensity = 0.001f;
@@ -633,6 +658,7 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   float ms = 0;
   CUCK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->dNodes = out.nodes; c->dPacked = out.packed; c->nNodes = out.nNodes; c->nValid = out.nValid;
+  for (int k = 0; k < 3; ++k) { c->sceneLo[k] = out.sceneLo[k]; c->sceneHi[k] = out.sceneHi[k]; }
   c->msBuild = ms;
   c->accelFlags = flags;
   c->built = true;

@@ -225,6 +225,16 @@ __device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const f
   c.pb.state[path] = childState;
   uint32_t pos = queuePush(c.pb.counters + C_NEXT);
   c.pb.qNext[pos] = path;
+  if (c.pb.qKey) {
+    // reordering key: 21-bit Morton cell of the origin (7 bits/axis of the scene box) | direction octant
+    uint32_t x = (uint32_t)fminf(fmaxf((o.x - c.sceneLo.x) * c.sceneInvExt.x, 0.f), 127.f);
+    uint32_t y = (uint32_t)fminf(fmaxf((o.y - c.sceneLo.y) * c.sceneInvExt.y, 0.f), 127.f);
+    uint32_t z = (uint32_t)fminf(fmaxf((o.z - c.sceneLo.z) * c.sceneInvExt.z, 0.f), 127.f);
+    auto spread = [](uint32_t v) { v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+    uint32_t cell = (spread(x) << 2) | (spread(y) << 1) | spread(z);
+    uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
+    c.pb.qKey[pos] = (cell << 3) | oct;
+  }
 }
 
 // lambertian (Material.cu:28-43) and metal (:49-66)
@@ -275,8 +285,11 @@ __global__ void __launch_bounds__(TPB) k_shade_dielectric(LaunchCtx c, uint32_t 
 
 // disney/NORMAL (Material.cu:170-222)
 constexpr int DISNEY_TPB = 128;
+#ifndef MOX_DISNEY_MINBLOCKS
+#define MOX_DISNEY_MINBLOCKS 6
+#endif
 template <int RM>
-__global__ void __launch_bounds__(DISNEY_TPB, 6) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
+__global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
   uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
   if (i >= count) return;
   ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DISNEY][i], depth);

@@ -19,6 +19,10 @@ struct PathBuffers {
   float4 *rayO = nullptr, *rayD = nullptr, *hit = nullptr, *thr = nullptr, *rad = nullptr;
   int* state = nullptr;
   uint32_t *qCur = nullptr, *qNext = nullptr;
+  uint32_t* qBuf[3] = {nullptr, nullptr, nullptr};   // queue storage; qCur / qNext point into it
+  uint32_t* kBuf[2] = {nullptr, nullptr};            // sort keys of qNext (ray reordering) + scratch
+  uint32_t* qKey = nullptr;                          // keys written next to qNext (null: reordering off)
+  uint32_t* sortScratch = nullptr;
   uint32_t* qMat[Q_COUNT] = {nullptr, nullptr, nullptr, nullptr};
   float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;  // shadow rays: origin per Disney path, (dir, tmax) and contribution per slot
   uint32_t* shQueue = nullptr;                            // slots that need a shadow ray
@@ -35,6 +39,7 @@ struct LaunchCtx {
   uint32_t nOwned;
   float* accu;               // device W*H*3
   bool countTraversal;
+  float3 sceneLo, sceneInvExt;  // ray-reordering key: 7-bit cell of the origin inside the scene box
   cudaStream_t stream;
 };
 
