@@ -296,7 +296,10 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
   const size_t P = (size_t)S * c->nOwned;
   if (P == 0) return MOX_OK;
   if (P > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "batch too large");
-  int rc = ensurePaths(c, P, c->lights.size(), S);
+  // Size the wavefront buffers for a full batch right away (not for this call's sample count), so
+  // a later call with more samples per pixel does not reallocate inside its timed region.
+  const size_t fullBatch = std::max<size_t>(1, c->maxBatchPaths / c->nOwned) * (size_t)c->nOwned;
+  int rc = ensurePaths(c, std::max(P, fullBatch), c->lights.size(), std::max<size_t>(S, fullBatch / c->nOwned));
   if (rc) return rc;
   PathBuffers& pb = c->pb;
   CUCK(c, cudaMemcpyAsync(pb.seeds, seeds.data(), S * 4, cudaMemcpyHostToDevice, c->stream));
