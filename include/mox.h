@@ -137,6 +137,11 @@ int mox_add_mesh(mox_ctx*, const float* vertices, size_t n_vertices, const float
                  const int32_t* vIdx, const int32_t* nIdx, const int32_t* tIdx, size_t n_faces,
                  int material_kind, const void* material_params, uint32_t* out_first_prim_id);
 
+/* videoParams.spheres[i]["sphereParams"]->setUserData (MinimalOptiX.cpp:762-764): move / resize a
+ * sphere added earlier.  The acceleration structure must be rebuilt (mox_build_accel) before the
+ * next launch. */
+int mox_update_sphere(mox_ctx*, uint32_t prim_id, const SphereParams*);
+
 /* context["lights"] buffer used by the Disney NEE loop (MinimalOptiX.cpp:523-531,
  * Material.cu:116,172). */
 int mox_set_lights(mox_ctx*, const LightParams*, size_t n);
@@ -171,6 +176,10 @@ int mox_read_accum(mox_ctx*, float* dst_rgb);
 int mox_map_accum(mox_ctx*, const float** out);
 int mox_unmap_accum(mox_ctx*);
 int mox_clear_accum(mox_ctx*);
+/* Resume: load a previously read accumulation buffer (W*H*3 floats) and continue the seed schedule
+ * of mox_render at launch index `launches` (the reference has snapshots but no reload,
+ * MinimalOptiX.cpp:543-558; this is the "dump/resume" row of SURVEY.md §8 f-2). */
+int mox_set_accum(mox_ctx*, const float* src_rgb, uint64_t launches);
 
 /* Multi-GPU gather plumbing (device pointers on this context's GPU).
  * mox_owned_pixels: number of pixels rank `rank` of the current partition owns.

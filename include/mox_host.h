@@ -64,6 +64,12 @@ int moxh_scene_mesh_data(const moxh_scene*, uint32_t mesh, const float** v, cons
 int moxh_scene_upload(const moxh_scene*, const moxh_api*, void* ctx, uint32_t width, uint32_t height,
                       uint32_t max_depth);
 
+/* Bouncing-sphere animation (MinimalOptiX::animate, MinimalOptiX.cpp:562-590): advance the sphere
+ * items by `time` seconds, then push the new SphereParams through <prefix>update_sphere.  The caller
+ * rebuilds the acceleration structure (mox_build_accel) before the next launch. */
+int moxh_scene_animate(moxh_scene*, float time);
+int moxh_scene_apply_spheres(const moxh_scene*, const moxh_api*, void* ctx);
+
 /* updateContent (MinimalOptiX.cpp:43-66): out[H-1-i][j] = quantise(clamp(accu[i][j] / n, 0, 1)),
  * quantise(v) = round(v * 65535) >> 8 (QColor::setRedF -> RGB888).  out: W*H*3 bytes, row 0 = top. */
 void moxh_accum_to_rgb8(const float* accum, uint32_t width, uint32_t height, float n_accum, uint8_t* out);

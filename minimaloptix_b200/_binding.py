@@ -41,6 +41,8 @@ SIGNATURES = {
     "map_accum": (C.c_int, [_vp, C.POINTER(_fp)]),
     "unmap_accum": (C.c_int, [_vp]),
     "clear_accum": (C.c_int, [_vp]),
+    "set_accum": (C.c_int, [_vp, _vp, _u64]),
+    "update_sphere": (C.c_int, [_vp, _u32, C.POINTER(S.SphereParams)]),
     "owned_pixels": (C.c_int, [_vp, _u32, C.POINTER(_u64)]),
     "pack_owned": (C.c_int, [_vp, _vp]),
     "unpack_owned": (C.c_int, [_vp, _u32, _vp]),
@@ -196,6 +198,13 @@ class Context:
         p = _fp()
         self._ck(self.b.map_accum(self.h, C.byref(p)), "map_accum")
         return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))
+
+    def set_accum(self, accum, launches):
+        a = _f32c(accum)
+        self._ck(self.b.set_accum(self.h, _ptr(a), launches), "set_accum")
+
+    def update_sphere(self, prim_id, sphere):
+        self._ck(self.b.update_sphere(self.h, prim_id, C.byref(sphere)), "update_sphere")
 
     def clear_accum(self):
         self._ck(self.b.clear_accum(self.h), "clear_accum")

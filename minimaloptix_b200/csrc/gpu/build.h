@@ -5,6 +5,31 @@
 #include <algorithm>
 #include "gpu_types.h"
 
+// Grow-only device scratch shared by successive builds (per-frame rebuilds of an animated scene
+// must not pay ~25 cudaMalloc/cudaFree pairs).  take() hands out 256-byte aligned slices.
+struct DeviceArena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  unsigned long long* pinned = nullptr;  // 8 bytes of pinned host memory for small read-backs
+  bool reserve(size_t bytes) {
+    off = 0;
+    if (bytes <= cap) return true;
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0;
+    if (cudaMalloc(&base, bytes) != cudaSuccess) return false;
+    cap = bytes;
+    return true;
+  }
+  template <class T> T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > cap) return nullptr;
+    T* p = (T*)(base + off);
+    off += bytes;
+    return p;
+  }
+  void release() { if (base) cudaFree(base); if (pinned) cudaFreeHost(pinned); base = nullptr; pinned = nullptr; cap = off = 0; }
+};
+
 struct BuildInput {
   int nPrims = 0;
   const PrimDesc* prims = nullptr;     // device
@@ -12,6 +37,7 @@ struct BuildInput {
   const float* verts = nullptr;        // device
   const Analytic* analytic = nullptr;  // device
   cudaEvent_t evStart = nullptr, evStop = nullptr;  // recorded around the build kernels when set
+  DeviceArena* arena = nullptr;  // required
   bool usePloc = true;   // false: Karras radix tree (fastest build, lower quality)
   int plocRadius = 16;
 };
@@ -27,15 +53,18 @@ struct PlocScratch {
   unsigned long long* tileSums = nullptr;
   unsigned long long* hostTotal = nullptr;  // pinned
 };
-bool plocAlloc(PlocScratch& s, int n, std::string& err);
-void plocFree(PlocScratch& s);
+size_t plocScratchBytes(int n);
+bool plocAlloc(PlocScratch& s, int n, DeviceArena& arena, std::string& err);
 bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* primLo, const float4* primHi, int radius,
                BvhNode2* outNodes, float rootLo[3], float rootHi[3], int* maxDepthOut, cudaStream_t stream, std::string& err);
 
 struct BuildOutput {
-  BvhNode2* nodes = nullptr;  // device, owned by the caller after a successful build
+  // device, owned by the caller.  On entry they may hold buffers of nodesCap / packedCap records from a
+  // previous build, which are reused when large enough.
+  BvhNode2* nodes = nullptr;
   int nNodes = 0;
-  float4* packed = nullptr;   // device, 3 float4 per valid primitive in leaf order
+  float4* packed = nullptr;   // 3 float4 per valid primitive in leaf order
+  size_t nodesCap = 0, packedCap = 0;
   int nValid = 0, nInvalid = 0;
   int iterations = 0;
   bool usedPloc = false;  // false: Karras radix tree (requested, or PLOC fallback because of depth)

@@ -370,13 +370,32 @@ inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::string& err) {
   const int n = in.nPrims;
-  out = BuildOutput();
+  {  // keep the caller's reusable buffers, reset everything else
+    BuildOutput fresh;
+    fresh.nodes = out.nodes; fresh.packed = out.packed; fresh.nodesCap = out.nodesCap; fresh.packedCap = out.packedCap;
+    out = fresh;
+  }
+  DeviceArena& arena = *in.arena;
+  if (!arena.pinned && cudaMallocHost(&arena.pinned, 8) != cudaSuccess) { err = "cudaMallocHost failed"; return false; }
+  // persistent outputs: reuse the previous build's buffers when they are large enough
+  auto ensureOut = [&](size_t nodesNeeded, size_t packedNeeded) -> bool {
+    if (out.nodesCap < nodesNeeded || !out.nodes) {
+      cudaFree(out.nodes); out.nodes = nullptr; out.nodesCap = 0;
+      if (cudaMalloc(&out.nodes, nodesNeeded * sizeof(BvhNode2)) != cudaSuccess) return false;
+      out.nodesCap = nodesNeeded;
+    }
+    if (out.packedCap < packedNeeded || !out.packed) {
+      cudaFree(out.packed); out.packed = nullptr; out.packedCap = 0;
+      if (cudaMalloc(&out.packed, packedNeeded * 48) != cudaSuccess) return false;
+      out.packedCap = packedNeeded;
+    }
+    return true;
+  };
   if (n == 0) {  // empty scene: a root with two empty children
     BvhNode2 root;
     root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);  // empty children: a point box no ray reaches
     root.ref = make_int4(MOX_EMPTY_CHILD, MOX_EMPTY_CHILD, 0, 0);
-    CK(cudaMalloc(&out.nodes, sizeof(BvhNode2)));
-    CK(cudaMalloc(&out.packed, 48));
+    if (!ensureOut(1, 1)) { err = "out of device memory"; return false; }
     CK(cudaMemcpy(out.nodes, &root, sizeof root, cudaMemcpyHostToDevice));
     out.nNodes = 1;
     if (in.evStart) CK(cudaEventRecord(in.evStart, stream));
@@ -395,31 +414,29 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   // small: [0..5] centroid bounds, [6] invalid count, [7] error flag, [8..11] tile counters, [16..16+1024) histograms
   const size_t smallWords = 16 + 1024;
   PlocScratch ploc;
-  auto freeScratch = [&]() {
-    plocFree(ploc);
-    cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(small); cudaFree(status);
-    cudaFree(boxLo); cudaFree(boxHi); cudaFree(children); cudaFree(range); cudaFree(parentInternal);
-    cudaFree(parentLeaf); cudaFree(nodeLo); cudaFree(nodeHi); cudaFree(arrivals);
-    out.scratchLo = out.scratchHi = nullptr;
-  };
-  auto bail = [&](const std::string& what) { freeScratch(); cudaFree(out.nodes); cudaFree(out.packed); out.nodes = nullptr; out.packed = nullptr; err = what; return false; };
+  auto freeScratch = [&]() { out.scratchLo = out.scratchHi = nullptr; };  // the arena keeps the memory for the next build
+  auto bail = [&](const std::string& what) { freeScratch(); err = what; return false; };
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
-  // All allocations happen before the first kernel so that the timed build is kernels only.
-  CKB(cudaMalloc(&boxLo, (size_t)n * 16)); CKB(cudaMalloc(&boxHi, (size_t)n * 16));
-  CKB(cudaMalloc(&keysA, (size_t)n * 4)); CKB(cudaMalloc(&keysB, (size_t)n * 4));
-  CKB(cudaMalloc(&valsA, (size_t)n * 4)); CKB(cudaMalloc(&valsB, (size_t)n * 4));
-  CKB(cudaMalloc(&small, smallWords * 4));
-  CKB(cudaMalloc(&status, (size_t)4 * nTiles * 256 * 4));
-  CKB(cudaMalloc(&children, (size_t)nInnerMax * 8)); CKB(cudaMalloc(&range, (size_t)nInnerMax * 8));
-  CKB(cudaMalloc(&parentInternal, (size_t)nInnerMax * 4)); CKB(cudaMalloc(&parentLeaf, (size_t)n * 4));
-  CKB(cudaMalloc(&nodeLo, (size_t)nInnerMax * 16)); CKB(cudaMalloc(&nodeHi, (size_t)nInnerMax * 16));
-  CKB(cudaMalloc(&arrivals, (size_t)nInnerMax * 4));
-  CKB(cudaMalloc(&out.nodes, (size_t)nInnerMax * sizeof(BvhNode2)));
-  CKB(cudaMalloc(&out.packed, (size_t)n * 48));
+  // All memory is in place before the first kernel so that the timed build is kernels only.
+  const size_t nn = (size_t)n, ni = (size_t)nInnerMax;
+  size_t scratchBytes = nn * (2 * 16 + 4 * 4 + 4) + smallWords * 4 + (size_t)4 * nTiles * 256 * 4 + ni * (8 + 8 + 4 + 16 + 16 + 4) + 20 * 256;
+  if (in.usePloc && n >= 2) scratchBytes += plocScratchBytes(n);
+  if (!arena.reserve(scratchBytes)) return bail("out of device memory (build scratch)");
+  boxLo = arena.take<float4>(nn); boxHi = arena.take<float4>(nn);
+  keysA = arena.take<uint32_t>(nn); keysB = arena.take<uint32_t>(nn);
+  valsA = arena.take<uint32_t>(nn); valsB = arena.take<uint32_t>(nn);
+  small = arena.take<uint32_t>(smallWords);
+  status = arena.take<uint32_t>((size_t)4 * nTiles * 256);
+  children = arena.take<int2>(ni); range = arena.take<int2>(ni);
+  parentInternal = arena.take<int>(ni); parentLeaf = arena.take<int>(nn);
+  nodeLo = arena.take<float4>(ni); nodeHi = arena.take<float4>(ni);
+  arrivals = arena.take<uint32_t>(ni);
+  if (!arrivals) return bail("build arena too small");
+  if (!ensureOut(ni, nn)) return bail("out of device memory (BVH)");
   out.scratchLo = boxLo; out.scratchHi = boxHi;
   if (in.usePloc && n >= 2) {
     std::string perr;
-    if (!plocAlloc(ploc, n, perr)) return bail(perr);
+    if (!plocAlloc(ploc, n, arena, perr)) return bail(perr);
   }
   if (in.evStart) CKB(cudaEventRecord(in.evStart, stream));
 

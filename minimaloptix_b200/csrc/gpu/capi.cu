@@ -78,6 +78,8 @@ struct mox_ctx {
   DevBuf dTexObjs;
   BvhNode2* dNodes = nullptr;
   float4* dPacked = nullptr;
+  size_t nodesCap = 0, packedCap = 0;
+  DeviceArena buildArena;
   int nNodes = 0, nValid = 0;
   bool built = false, lightsDirty = true;
   uint32_t accelFlags = 0;
@@ -469,6 +471,7 @@ void mox_destroy(mox_ctx* c) {
   for (auto& b : c->otherOwned) b.release();
   freeTextures(c);
   c->dTexObjs.release();
+  c->buildArena.release();
   cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dAccu); cudaFree(c->dOwned);
   freePaths(c->pb);
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -642,9 +645,8 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   for (auto& m : c->mats)
     if (m.kind == MOX_MAT_DISNEY && (m.dis.albedoID < 0 || m.dis.albedoID > (int)c->textures.size()))
       return fail(c, MOX_ERR_INVALID, "DisneyParams.albedoID refers to a texture that was not added");
-  cudaFree(c->dNodes); cudaFree(c->dPacked);
-  c->dNodes = nullptr; c->dPacked = nullptr;
   BuildInput in;
+  in.arena = &c->buildArena;
   in.nPrims = (int)c->prims.size();
   in.prims = (const PrimDesc*)c->dPrims.p;
   in.tris = (const TriIdx*)c->dTris.p;
@@ -655,8 +657,11 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   if (const char* env = getenv("MOX_PLOC_RADIUS")) in.plocRadius = atoi(env);
   if (const char* env = getenv("MOX_FORCE_LBVH")) { if (atoi(env)) in.usePloc = false; }
   BuildOutput out;
+  out.nodes = c->dNodes; out.packed = c->dPacked; out.nodesCap = c->nodesCap; out.packedCap = c->packedCap;
   std::string err;
-  if (!buildBvh(in, out, c->stream, err)) return fail(c, MOX_ERR_CUDA, "build_accel: " + err);
+  bool okBuild = buildBvh(in, out, c->stream, err);
+  c->dNodes = out.nodes; c->dPacked = out.packed; c->nodesCap = out.nodesCap; c->packedCap = out.packedCap;
+  if (!okBuild) return fail(c, MOX_ERR_CUDA, "build_accel: " + err);
   CUCK(c, cudaEventSynchronize(c->ev1));
   float ms = 0;
   CUCK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -719,6 +724,24 @@ int mox_clear_accum(mox_ctx* c) {
   c->msRender = 0;
   for (double& m : c->msStage) m = 0;
   c->extendLaunches = c->kernelLaunches = 0;
+  return MOX_OK;
+}
+
+int mox_set_accum(mox_ctx* c, const float* src, uint64_t launches) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!src || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
+  int rc = bind(c);
+  if (rc) return rc;
+  CUCK(c, cudaMemcpy(c->dAccu, src, (size_t)c->accuW * c->accuH * 12, cudaMemcpyHostToDevice));
+  c->launches = launches;
+  return MOX_OK;
+}
+
+int mox_update_sphere(mox_ctx* c, uint32_t prim_id, const SphereParams* s) {
+  if (!c) return MOX_ERR_INVALID;
+  if (!s || prim_id >= c->prims.size() || (c->prims[prim_id].typeMat & 3u) != PT_SPHERE) return fail(c, MOX_ERR_INVALID, "not a sphere primitive");
+  c->analytic[c->prims[prim_id].geom].a = make_float4(s->center.x, s->center.y, s->center.z, s->radius);
+  c->built = false;
   return MOX_OK;
 }
 

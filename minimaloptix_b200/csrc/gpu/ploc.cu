@@ -246,27 +246,27 @@ inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 #define PCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
-bool plocAlloc(PlocScratch& s, int n, std::string& err) {
+size_t plocScratchBytes(int n) {
   const size_t nn = (size_t)std::max(n, 2);
-  PCK(cudaMalloc(&s.cid[0], nn * 4)); PCK(cudaMalloc(&s.cid[1], nn * 4));
-  PCK(cudaMalloc(&s.cLo[0], nn * 16)); PCK(cudaMalloc(&s.cLo[1], nn * 16));
-  PCK(cudaMalloc(&s.cHi[0], nn * 16)); PCK(cudaMalloc(&s.cHi[1], nn * 16));
-  PCK(cudaMalloc(&s.nn, nn * 4));
-  PCK(cudaMalloc(&s.nodeLo, 2 * nn * 16)); PCK(cudaMalloc(&s.nodeHi, 2 * nn * 16));
-  PCK(cudaMalloc(&s.children, nn * 8));
-  PCK(cudaMalloc(&s.parent, 2 * nn * 4)); PCK(cudaMalloc(&s.size, 2 * nn * 4));
-  PCK(cudaMalloc(&s.leafPos, nn * 4)); PCK(cudaMalloc(&s.orderedIds, nn * 4));
-  PCK(cudaMalloc(&s.tileSums, (size_t)(divUp(nn, PL_TILE) + 2) * 8));
-  PCK(cudaMallocHost(&s.hostTotal, 8));
-  return true;
+  // 2 cid + nn + parent(2) + size(2) + leafPos + orderedIds = 9 words, 4 cluster boxes + 2x2 node boxes = 8 float4,
+  // children 8 B, tile sums; plus alignment slack for 16 slices
+  return nn * (9 * 4 + 8 * 16 + 8) + (size_t)(divUp(nn, PL_TILE) + 2) * 8 + 16 * 256;
 }
 
-void plocFree(PlocScratch& s) {
-  for (int k = 0; k < 2; ++k) { cudaFree(s.cid[k]); cudaFree(s.cLo[k]); cudaFree(s.cHi[k]); }
-  cudaFree(s.nn); cudaFree(s.nodeLo); cudaFree(s.nodeHi); cudaFree(s.children); cudaFree(s.parent); cudaFree(s.size);
-  cudaFree(s.leafPos); cudaFree(s.orderedIds); cudaFree(s.tileSums);
-  if (s.hostTotal) cudaFreeHost(s.hostTotal);
-  s = PlocScratch();
+bool plocAlloc(PlocScratch& s, int n, DeviceArena& a, std::string& err) {
+  const size_t nn = (size_t)std::max(n, 2);
+  s.cid[0] = a.take<uint32_t>(nn); s.cid[1] = a.take<uint32_t>(nn);
+  s.cLo[0] = a.take<float4>(nn); s.cLo[1] = a.take<float4>(nn);
+  s.cHi[0] = a.take<float4>(nn); s.cHi[1] = a.take<float4>(nn);
+  s.nn = a.take<uint32_t>(nn);
+  s.nodeLo = a.take<float4>(2 * nn); s.nodeHi = a.take<float4>(2 * nn);
+  s.children = a.take<uint2>(nn);
+  s.parent = a.take<uint32_t>(2 * nn); s.size = a.take<uint32_t>(2 * nn);
+  s.leafPos = a.take<uint32_t>(nn); s.orderedIds = a.take<uint32_t>(nn);
+  s.tileSums = a.take<unsigned long long>((size_t)divUp(nn, PL_TILE) + 2);
+  s.hostTotal = a.pinned;
+  if (!s.tileSums || !s.hostTotal) { err = "PLOC scratch does not fit the build arena"; return false; }
+  return true;
 }
 
 // n >= 2 valid primitives in Morton order (sortedIds); primLo/primHi indexed by primitive id.

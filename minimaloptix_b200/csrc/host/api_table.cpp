@@ -15,7 +15,7 @@ bool loadMoxApi(const char* libPath, const char* prefix, MoxApi& api, std::strin
   BIND(create); BIND(destroy); BIND(last_error); BIND(set_globals); BIND(set_camera); BIND(set_rng_mode);
   BIND(set_partition); BIND(add_texture_rgba32f); BIND(add_sphere); BIND(add_quad); BIND(add_mesh);
   BIND(set_lights); BIND(clear_scene); BIND(build_accel); BIND(launch); BIND(render); BIND(read_accum);
-  BIND(clear_accum); BIND(get_stats);
+  BIND(clear_accum); BIND(get_stats); BIND(set_accum); BIND(update_sphere);
 #undef BIND
   return ok;
 }

@@ -27,6 +27,8 @@ struct MoxApi {
   int (*read_accum)(mox_ctx*, float*) = nullptr;
   int (*clear_accum)(mox_ctx*) = nullptr;
   int (*get_stats)(mox_ctx*, mox_stats*) = nullptr;
+  int (*set_accum)(mox_ctx*, const float*, uint64_t) = nullptr;
+  int (*update_sphere)(mox_ctx*, uint32_t, const SphereParams*) = nullptr;
 };
 
 // prefix is "mox_" for the product library.  Returns false and fills err on failure.

@@ -17,7 +17,7 @@
 static void usage() {
   fprintf(stderr,
           "usage: mox_cli --scene NAME [--scene-dir DIR] [--width W --height H] [--spp N] [--max-depth D]\n"
-          "               [--seed S] [--rng ref|philox] [--out PREFIX] [--snapshots] [--dump-accum] [--device K]\n"
+          "               [--seed S] [--rng ref|philox] [--out PREFIX] [--snapshots] [--dump-accum] [--resume FILE.moxa] [--device K]\n"
           "               [--param P] [--lib PATH]\n"
           "  NAME: spheres_lens spheres_pinhole random_spheres interior soup, or a folder under DIR\n"
           "        holding NAME.scene (coffee, cornell, ...).  Defaults are the reference's constants\n"
@@ -25,7 +25,7 @@ static void usage() {
 }
 
 int main(int argc, char** argv) {
-  std::string scene = "spheres_lens", dir = "scenes", out = "out", lib, rng = "ref";
+  std::string scene = "spheres_lens", dir = "scenes", out = "out", lib, rng = "ref", resume;
   uint32_t W = 0, H = 0, spp = 32, depth = 256, seed = 0xC0FFEE;
   uint64_t param = 0;
   int device = 0;
@@ -44,6 +44,7 @@ int main(int argc, char** argv) {
     else if (a == "--out") out = val();
     else if (a == "--snapshots") snapshots = true;
     else if (a == "--dump-accum") dumpAccum = true;
+    else if (a == "--resume") resume = val();
     else if (a == "--device") device = atoi(val());
     else if (a == "--param") param = strtoull(val(), nullptr, 0);
     else if (a == "--lib") lib = val();
@@ -83,8 +84,15 @@ int main(int argc, char** argv) {
     moxh_accum_to_rgb8(accum.data(), W, H, (float)n, rgb.data());
     if (moxh_write_image((name + ".png").c_str(), rgb.data(), W, H)) fprintf(stderr, "write: %s\n", moxh_last_error());
   };
-  auto t0 = std::chrono::steady_clock::now();
   uint32_t done = 0, checkpoint = 1;
+  if (!resume.empty()) {  // continue a previous run: same seed schedule, samples [launches, spp)
+    uint64_t launches = 0;
+    if (moxh_read_accum(resume.c_str(), accum.data(), W, H, &launches)) { fprintf(stderr, "resume: %s\n", moxh_last_error()); return 1; }
+    if (api.set_accum(ctx, accum.data(), launches)) { fprintf(stderr, "set_accum: %s\n", api.last_error(ctx)); return 1; }
+    done = (uint32_t)std::min<uint64_t>(launches, spp);
+    while (checkpoint <= done) checkpoint *= 2;
+  }
+  auto t0 = std::chrono::steady_clock::now();
   while (done < spp) {  // renderScene: snapshots at 1, 2, 4, ... (MinimalOptiX.cpp:543-553)
     uint32_t n = snapshots ? std::min(spp, checkpoint) - done : spp - done;
     if (api.render(ctx, n, seed)) { fprintf(stderr, "render: %s\n", api.last_error(ctx)); return 1; }

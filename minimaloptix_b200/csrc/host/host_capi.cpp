@@ -143,6 +143,17 @@ int moxh_scene_upload(const moxh_scene* s, const moxh_api* api, void* ctx, uint3
   return 0;
 }
 
+int moxh_scene_animate(moxh_scene* s, float time) {
+  if (!s) return fail("bad argument");
+  animateSpheres(s->d, time);
+  return 0;
+}
+int moxh_scene_apply_spheres(const moxh_scene* s, const moxh_api* api, void* ctx) {
+  if (!s || !api || !ctx) return fail("bad argument");
+  std::string err;
+  return applySpheres(s->d, api->t, (mox_ctx*)ctx, err) ? 0 : fail(err);
+}
+
 void moxh_accum_to_rgb8(const float* accum, uint32_t w, uint32_t h, float n, uint8_t* out) { accumToRgb8(accum, w, h, n, out); }
 int moxh_write_image(const char* path, const uint8_t* rgb, uint32_t w, uint32_t h) {
   std::string err;

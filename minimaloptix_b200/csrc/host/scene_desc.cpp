@@ -485,6 +485,51 @@ bool buildSoup(SceneDesc& s, uint64_t nTris, uint64_t seed) {
   return true;
 }
 
+// ------------------------------------------------------------------ animation
+namespace {
+const float kGravity = 4000.f, kRestitution = 0.9f, kFloorY = -0.5f;
+
+// One sphere, `time` seconds: free fall until the floor plane, then a damped bounce.
+void moveSphere(SphereParams& p, float time, int depth = 0) {
+  float fall = p.velocity.y * time + time * time * kGravity / 2.0f;  // distance travelled downwards
+  float room = p.center.y - p.radius - kFloorY;                      // height above the floor
+  if (fall < room) {
+    p.center.x += p.velocity.x * time;
+    p.center.z += p.velocity.z * time;
+    p.center.y -= fall;
+    p.velocity.y += kGravity * time;
+    return;
+  }
+  float vend = sqrtf(p.velocity.y * p.velocity.y + 2.0f * kGravity * room);  // speed at impact
+  float t = (vend - p.velocity.y) / kGravity;                                // time to impact
+  if (t < 1e-6f || depth > 64) {  // resting on the floor
+    p.velocity.y = 0.f;
+    p.center.y = kFloorY + p.radius;
+    return;
+  }
+  p.center.x += p.velocity.x * t;
+  p.center.z += p.velocity.z * t;
+  p.center.y = kFloorY + p.radius;
+  p.velocity.x *= kRestitution;
+  p.velocity.y = -vend * kRestitution;  // velocity.y is positive downwards
+  moveSphere(p, time - t, depth + 1);
+}
+}  // namespace
+
+void animateSpheres(SceneDesc& s, float time) {
+  for (Item& it : s.items)
+    if (it.type == Item::SPHERE_ITEM && it.mat.kind != MOX_MAT_LIGHT) moveSphere(it.sphere, time);
+}
+
+bool applySpheres(const SceneDesc& s, const MoxApi& api, mox_ctx* ctx, std::string& err) {
+  uint32_t prim = 0;
+  for (const Item& it : s.items) {
+    if (it.type == Item::SPHERE_ITEM && api.update_sphere(ctx, prim, &it.sphere)) { err = std::string("update_sphere: ") + api.last_error(ctx); return false; }
+    prim += it.type == Item::MESH_ITEM ? (uint32_t)s.meshes[it.mesh].faces() : 1u;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------ upload through the C ABI
 bool uploadScene(const SceneDesc& s, const MoxApi& api, mox_ctx* ctx, uint32_t width, uint32_t height, uint32_t maxDepth,
                  std::string& err) {

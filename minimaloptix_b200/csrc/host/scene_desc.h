@@ -87,6 +87,12 @@ bool buildInterior(SceneDesc& out, uint64_t targetTris, uint32_t seed);
 // Random triangle soup in the unit cube (BASELINE config 5).
 bool buildSoup(SceneDesc& out, uint64_t nTris, uint64_t seed);
 
+// Bouncing-ball animation of the sphere items (MinimalOptiX::move / animate, MinimalOptiX.cpp:562-590):
+// gravity 4000, restitution 0.9, floor plane y = -0.5.  `time` is the frame step (the reference uses 0.002).
+void animateSpheres(SceneDesc& s, float time);
+// Re-send every sphere item through update_sphere (primitive ids follow item order).
+bool applySpheres(const SceneDesc& s, const MoxApi& api, mox_ctx* ctx, std::string& err);
+
 // Push a SceneDesc through the C ABI: set_globals, set_camera, add_* in item order, set_lights.
 // Reference defaults: eps 0.001, minIntensity 0.001, absorb 0, bad 1 (MinimalOptiX.h:85-89,
 // MinimalOptiX.cpp:136-151).

@@ -51,6 +51,8 @@ def lib():
         L.moxh_scene_mesh_hash.argtypes = [_vp, _u32, C.POINTER(_u64 * 4)]
         L.moxh_scene_mesh_data.argtypes = [_vp, _u32, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_int32))]
         L.moxh_scene_upload.argtypes = [_vp, _vp, _vp, _u32, _u32, _u32]
+        L.moxh_scene_animate.argtypes = [_vp, C.c_float]
+        L.moxh_scene_apply_spheres.argtypes = [_vp, _vp, _vp]
         L.moxh_accum_to_rgb8.argtypes = [_vp, _u32, _u32, C.c_float, _vp]
         L.moxh_write_image.argtypes = [C.c_char_p, _vp, _u32, _u32]
         L.moxh_write_accum.argtypes = [C.c_char_p, _vp, _u32, _u32, _u64]
@@ -174,6 +176,14 @@ class Scene:
         verts = np.ctypeslib.as_array(v, shape=(info["vertices"], 3)).copy()
         idx = np.ctypeslib.as_array(vi, shape=(info["faces"], 3)).copy()
         return verts, idx
+
+    def animate(self, time):
+        if lib().moxh_scene_animate(self.h, time) != 0:
+            raise MoxError(_err())
+
+    def apply_spheres(self, api_table, ctx):
+        if lib().moxh_scene_apply_spheres(self.h, api_table.h, ctx.h) != 0:
+            raise MoxError("moxh_scene_apply_spheres: " + _err())
 
     def texture_count(self):
         return lib().moxh_scene_texture_count(self.h)

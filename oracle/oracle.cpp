@@ -775,6 +775,18 @@ int orc_clear_accum(orc_ctx* c) {
   c->launches = 0; c->cnt = Counters{}; c->msRender = 0;
   return MOX_OK;
 }
+int orc_set_accum(orc_ctx* c, const float* src, uint64_t launches) {
+  if (!c || !src || c->accu.empty()) return MOX_ERR_INVALID;
+  std::copy(src, src + c->accu.size(), c->accu.begin());
+  c->launches = launches;
+  return MOX_OK;
+}
+int orc_update_sphere(orc_ctx* c, uint32_t prim, const SphereParams* s) {
+  if (!c || !s || prim >= c->prims.size() || c->prims[prim].type != PT_SPHERE) return MOX_ERR_INVALID;
+  c->spheres[c->prims[prim].geom] = *s;
+  c->built = false;
+  return MOX_OK;
+}
 int orc_owned_pixels(orc_ctx* c, uint32_t rank, uint64_t* out_n) {
   if (!c || !out_n || rank >= c->world) return MOX_ERR_INVALID;
   std::vector<uint32_t> l; ownedList(*c, rank, l); *out_n = l.size();

@@ -35,6 +35,8 @@ int orc_read_accum(orc_ctx*, float* dst_rgb);
 int orc_map_accum(orc_ctx*, const float** out);
 int orc_unmap_accum(orc_ctx*);
 int orc_clear_accum(orc_ctx*);
+int orc_set_accum(orc_ctx*, const float* src_rgb, uint64_t launches);
+int orc_update_sphere(orc_ctx*, uint32_t prim_id, const SphereParams*);
 int orc_owned_pixels(orc_ctx*, uint32_t rank, uint64_t* out_n);
 int orc_pack_owned(orc_ctx*, void* dst);            /* host pointers in the oracle */
 int orc_unpack_owned(orc_ctx*, uint32_t rank, const void* src);

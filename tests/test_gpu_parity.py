@@ -334,6 +334,41 @@ def test_tile_partition_union_is_bit_identical(host, api_tables, gpu_backend):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+def test_animated_spheres_rebuild_and_resume(host, api_tables, orc, gpu_backend):
+    """§8 f-2/f-3: move the spheres (reference animate()), update + rebuild on both sides, images
+    still agree; then dump / set_accum resumes the seed schedule bit-exactly."""
+    sc = host.Scene.builtin("random_spheres")
+    o, g = both(host, api_tables, orc, gpu_backend, sc, 160, 90, 5)
+    for _ in range(5):
+        sc.animate(0.002)
+    sc.apply_spheres(api_tables.oracle, o)
+    sc.apply_spheres(api_tables.gpu, g)
+    from minimaloptix_b200 import MoxError
+    with pytest.raises(MoxError):
+        g.launch(1)  # accel is stale after update_sphere
+    o.build_accel(); g.build_accel()
+    o.render(4, 5); g.render(4, 5)
+    rmse, within, rel = image_metrics(g.read_accum(), o.read_accum(), 4)
+    assert rmse <= 2e-3 and within >= 0.999
+    # the moved scene differs from the static one
+    s2 = host.Scene.builtin("random_spheres")
+    g2 = gpu_backend.context(0)
+    s2.upload(api_tables.gpu, g2, 160, 90, 5)
+    g2.build_accel(); g2.render(4, 5)
+    assert not np.array_equal(g2.read_accum(), g.read_accum())
+    # resume: 2 spp, dump, reload into a fresh context, 2 more == 4 spp in one go
+    g3 = gpu_backend.context(0)
+    s2.upload(api_tables.gpu, g3, 160, 90, 5)
+    g3.build_accel(); g3.render(2, 5)
+    half = g3.read_accum()
+    g4 = gpu_backend.context(0)
+    s2.upload(api_tables.gpu, g4, 160, 90, 5)
+    g4.build_accel()
+    g4.set_accum(half, 2)
+    g4.render(2, 5)
+    assert np.array_equal(g4.read_accum().view(np.uint32), g2.read_accum().view(np.uint32))
+
+
 def test_error_paths(host, api_tables, gpu_backend):
     from minimaloptix_b200 import MoxError
     g = gpu_backend.context(0)
