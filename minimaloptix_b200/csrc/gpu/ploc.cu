@@ -174,6 +174,78 @@ k_ploc_merge(int n, int nLeaves, uint32_t nodeBase, const uint32_t* __restrict__
   }
 }
 
+// All remaining iterations once at most PL_TAIL clusters are left: one block, clusters in shared
+// memory, no host round trips.  Same merge rule and the same scan-based node numbering as the
+// multi-kernel iterations above.
+constexpr int PL_TAIL = 1024;
+__global__ void __launch_bounds__(PL_TAIL)
+k_ploc_tail(int n, int nLeaves, int radius, uint32_t nodeBase, const uint32_t* __restrict__ cidIn, const float4* __restrict__ cLoIn,
+            const float4* __restrict__ cHiIn, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi, uint2* __restrict__ children,
+            uint32_t* __restrict__ parent, uint32_t* __restrict__ size, uint32_t* __restrict__ nodesCreated) {
+  __shared__ float4 sLo[PL_TAIL], sHi[PL_TAIL];
+  __shared__ uint32_t sId[PL_TAIL];
+  __shared__ int sNn[PL_TAIL];
+  __shared__ uint32_t sWarp[32][2];
+  const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+  if (i < n) { sId[i] = cidIn[i]; sLo[i] = cLoIn[i]; sHi[i] = cHiIn[i]; }
+  __syncthreads();
+  while (n > 1) {
+    float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+    int best = -1;
+    if (i < n) {
+      lo = sLo[i]; hi = sHi[i];
+      float bestA = __int_as_float(0x7f800000);
+      for (int o = -radius; o <= radius; ++o) {
+        int j = i + o;
+        if (o == 0 || j < 0 || j >= n) continue;
+        float a = mergedArea(lo, hi, sLo[j], sHi[j]);
+        if (a < bestA) { bestA = a; best = j; }
+      }
+      sNn[i] = best;
+    }
+    __syncthreads();
+    bool mutual = i < n && best >= 0 && sNn[best] == i;
+    bool merged = mutual && i < best, removed = mutual && i > best;
+    uint32_t valid = (i < n && !removed) ? 1u : 0u, mrg = merged ? 1u : 0u;
+    uint32_t myId = i < n ? sId[i] : 0u, otherId = merged ? sId[best] : 0u;
+    float4 olo = lo, ohi = hi;
+    if (merged) { olo = sLo[best]; ohi = sHi[best]; }
+    // block-wide exclusive scans of `valid` and `mrg`
+    uint32_t iv = valid, im = mrg;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t tv = __shfl_up_sync(0xffffffffu, iv, o), tm = __shfl_up_sync(0xffffffffu, im, o);
+      if (lane >= o) { iv += tv; im += tm; }
+    }
+    if (lane == 31) { sWarp[warp][0] = iv; sWarp[warp][1] = im; }
+    __syncthreads();
+    uint32_t offV = 0, offM = 0, totV = 0, totM = 0;
+    for (int w = 0; w < PL_TAIL / 32; ++w) {
+      if (w < warp) { offV += sWarp[w][0]; offM += sWarp[w][1]; }
+      totV += sWarp[w][0]; totM += sWarp[w][1];
+    }
+    uint32_t pos = offV + iv - valid, mpos = offM + im - mrg;
+    __syncthreads();  // everyone has read its inputs from shared memory
+    if (valid) {
+      if (merged) {
+        uint32_t node = nodeBase + mpos, id = (uint32_t)nLeaves + node;
+        float4 nlo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
+        float4 nhi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
+        children[node] = make_uint2(myId, otherId);
+        parent[myId] = id; parent[otherId] = id;
+        size[id] = size[myId] + size[otherId];
+        nodeLo[id] = nlo; nodeHi[id] = nhi;
+        sId[pos] = id; sLo[pos] = nlo; sHi[pos] = nhi;
+      } else {
+        sId[pos] = myId; sLo[pos] = lo; sHi[pos] = hi;
+      }
+    }
+    nodeBase += totM;
+    n = (int)totV;
+    __syncthreads();
+  }
+  if (i == 0) *nodesCreated = nodeBase;
+}
+
 // Position of the leftmost leaf of `node` in depth-first (leaf) order: walking up, every time we
 // are a right child the left sibling's whole subtree precedes us.
 __device__ __forceinline__ uint32_t leftmostPos(uint32_t node, uint32_t root, int nLeaves, const uint32_t* __restrict__ parent,
@@ -280,7 +352,7 @@ bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* p
   uint32_t nodeBase = 0;
   unsigned long long* dTotal = s.tileSums + divUp((size_t)std::max(n, 2), PL_TILE);
   int guard = 0;
-  while (count > 1) {
+  while (count > PL_TAIL) {
     int nTiles = divUp(count, PL_TILE);
     k_ploc_nn<<<divUp(count, PL_THREADS), PL_THREADS, 0, stream>>>(count, radius, s.cLo[cur], s.cHi[cur], s.nn);
     k_ploc_tile_sums<<<nTiles, PL_THREADS, 0, stream>>>(count, s.nn, s.tileSums);
@@ -297,6 +369,15 @@ bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* p
     nodeBase += merged;
     count = newCount;
     cur ^= 1;
+  }
+  if (count > 1) {
+    uint32_t* dCreated = (uint32_t*)(dTotal + 1) + 1;
+    k_ploc_tail<<<1, PL_TAIL, 0, stream>>>(count, n, radius, nodeBase, s.cid[cur], s.cLo[cur], s.cHi[cur], s.nodeLo, s.nodeHi, s.children,
+                                           s.parent, s.size, dCreated);
+    uint32_t created = 0;
+    PCK(cudaMemcpyAsync(&created, dCreated, 4, cudaMemcpyDeviceToHost, stream));
+    PCK(cudaStreamSynchronize(stream));
+    nodeBase = created;
   }
   const int nInner = n - 1;
   if ((int)nodeBase != nInner) { err = "PLOC node count mismatch"; return false; }
