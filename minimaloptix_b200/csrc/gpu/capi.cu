@@ -91,6 +91,7 @@ struct mox_ctx {
   uint32_t nOwned = 0;
   bool ownedDirty = true;
   std::vector<DevBuf> otherOwned;  // cached owned lists of other ranks (unpack)
+  std::vector<uint64_t> ownedCount; // cached |owned pixels| per rank of the current partition
 
   PathBuffers pb;
   float* pinned = nullptr;
@@ -180,6 +181,7 @@ int refreshOwned(mox_ctx* c) {
   c->nOwned = (uint32_t)l.size();
   for (auto& b : c->otherOwned) b.release();
   c->otherOwned.clear();
+  c->ownedCount.clear();
   c->ownedDirty = false;
   return MOX_OK;
 }
@@ -748,9 +750,13 @@ int mox_update_sphere(mox_ctx* c, uint32_t prim_id, const SphereParams* s) {
 int mox_owned_pixels(mox_ctx* c, uint32_t rank, uint64_t* out_n) {
   if (!c) return MOX_ERR_INVALID;
   if (!out_n || rank >= c->world || !c->haveGlobals) return fail(c, MOX_ERR_INVALID, "bad owned_pixels query");
-  std::vector<uint32_t> l;
-  ownedList(c->rp.W, c->rp.H, c->tile, c->world, rank, l);
-  *out_n = l.size();
+  // closed form: no need to enumerate the pixels
+  uint32_t W = c->rp.W, H = c->rp.H, T = c->tile, tx = (W + T - 1) / T, ty = (H + T - 1) / T;
+  uint64_t n = 0;
+  for (uint32_t j = 0; j < ty; ++j)
+    for (uint32_t i = 0; i < tx; ++i)
+      if ((i + j) % c->world == rank) n += (uint64_t)(std::min(W, (i + 1) * T) - i * T) * (std::min(H, (j + 1) * T) - j * T);
+  *out_n = n;
   return MOX_OK;
 }
 
@@ -771,15 +777,16 @@ int mox_unpack_owned(mox_ctx* c, uint32_t rank, const void* dev_src) {
   int rc = bind(c);
   if (rc) return rc;
   if ((rc = refreshOwned(c))) return rc;
-  if (c->otherOwned.size() != c->world) c->otherOwned.resize(c->world);
-  std::vector<uint32_t> l;
-  ownedList(c->rp.W, c->rp.H, c->tile, c->world, rank, l);
+  if (c->otherOwned.size() != c->world) { c->otherOwned.resize(c->world); c->ownedCount.assign(c->world, 0); }
   DevBuf& b = c->otherOwned[rank];
-  if (!b.p) {
+  if (!b.p) {  // first gather of this partition: build and upload rank's pixel list once
+    std::vector<uint32_t> l;
+    ownedList(c->rp.W, c->rp.H, c->tile, c->world, rank, l);
     if ((rc = ensure(c, b, l.size() * 4))) return rc;
     if (!l.empty()) CUCK(c, cudaMemcpy(b.p, l.data(), l.size() * 4, cudaMemcpyHostToDevice));
+    c->ownedCount[rank] = l.size();
   }
-  launchUnpackOwned(c->dAccu, (const uint32_t*)b.p, (uint32_t)l.size(), (const float*)dev_src, c->stream);
+  launchUnpackOwned(c->dAccu, (const uint32_t*)b.p, (uint32_t)c->ownedCount[rank], (const float*)dev_src, c->stream);
   CUCK(c, cudaStreamSynchronize(c->stream));
   return MOX_OK;
 }
