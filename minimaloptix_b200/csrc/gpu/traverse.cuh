@@ -75,6 +75,15 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
 }
 
 #define MOX_STACK MOX_TRAVERSAL_STACK
+// Ray / hit records are touched once per launch: stream them (evict-first) so they do not push
+// the BVH and the triangles out of L2.
+#ifdef MOX_NO_STREAM_HINTS
+#define MOX_LD_STREAM(p) __ldg(p)
+#define MOX_ST_STREAM(p, v) (*(p) = (v))
+#else
+#define MOX_LD_STREAM(p) __ldcs(p)
+#define MOX_ST_STREAM(p, v) __stcs((p), (v))
+#endif
 #define MOX_DONE ((int)0x80000000)   // sentinel "no more nodes" (same bit pattern as an empty child)
 #define MOX_FETCH_THRESHOLD 20       // refill a warp's idle lanes when fewer than this many are traversing
 
@@ -128,9 +137,9 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
         if (!active) {
           uint32_t i = base + __popc(idle & ltMask);
           if (i < jobCount) {
-            rayId = job.queue ? __ldg(job.queue + i) : i;
+            rayId = job.queue ? MOX_LD_STREAM(job.queue + i) : i;
             uint32_t oId = job.originMod ? rayId % job.originMod : rayId;
-            float4 ro = __ldg(job.rayO + oId), rd = __ldg(job.rayD + rayId);
+            float4 ro = MOX_LD_STREAM(job.rayO + oId), rd = MOX_LD_STREAM(job.rayD + rayId);
             if (!(ANYHIT && rd.w < 0.f)) {
               r = prepRay(mk3(ro), mk3(rd), ro.w);
               tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
@@ -222,7 +231,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
           float4 c = job.shC[rayId];
           job.shC[rayId] = make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w);
         } else {
-          job.hits[rayId] = make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma);
+          MOX_ST_STREAM(job.hits + rayId, make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma));
         }
         if (COUNT) {
           atomicAdd((unsigned long long*)(job.counters + 10), (unsigned long long)nv);
