@@ -256,8 +256,8 @@ def main():
         dist.all_reduce(ce, op=dist.ReduceOp.SUM)
     e2e_value = ce.item() / te.item() / 1e6
 
-    # ---- counting pass for the algorithmic bytes of the traversal kernel (untimed)
-    roofline = None
+    # ---- counting pass for the algorithmic bytes of the traversal kernels (untimed)
+    roofline = roofline_shadow = None
     if rank == 0:
         cctx = mox.gpu().context(local)
         sc.upload(api, cctx, W, H, MAX_DEPTH)
@@ -265,26 +265,42 @@ def main():
         cctx.build_accel(mox.structs.ACCEL_COUNTERS)
         cctx.render(1, SEED)
         cs = cctx.stats()
-        crays = rays_of(cs)
-        n_node = cs["node_visits"] / max(crays, 1)
-        n_prim = cs["prim_tests"] / max(crays, 1)
-        b_ray = 32 + 16 + n_node * cs["node_bytes"] + n_prim * cs["prim_bytes"]
-        peaks = {}
+        peaks, traffic = {}, {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+        except Exception:
+            pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json, HBM copy)" if "hbm_gbs" in peaks else "fallback"
+
+        def roof(kernel, key, rays_counted, nodes, prims, fixed_bytes, rays_timed, ms, launches):
+            n_node, n_prim = nodes / max(rays_counted, 1), prims / max(rays_counted, 1)
+            b_ray = fixed_bytes + n_node * cs["node_bytes"] + n_prim * cs["prim_bytes"]
+            achieved = rays_timed * b_ray / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            t = traffic.get(key, {})
+            return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": t.get("dram_bytes_per_launch"),
+                    "traffic_note": "dram__bytes_read+write per launch from the committed ncu --set full capture (1 spp per wavefront; "
+                                    "this run batches %d spp per launch)" % SPP_PER_STEP if t else None,
+                    "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim, "node_bytes": cs["node_bytes"],
+                    "prim_bytes": cs["prim_bytes"], "rays_per_s": rays_timed / (ms * 1e-3) if ms > 0 else 0.0,
+                    "launches": launches, "avg_launch_ms": ms / max(launches, 1),
+                    "share_of_step": ms / max(s1["ms_render"] - s0["ms_render"], 1e-9),
+                    "note": "BVH + triangles are L2-resident (126 MB L2): the algorithmic bytes are served by L2, DRAM traffic is far "
+                            "smaller; ncu shows the kernel latency/issue-bound (profiles/r1_final_kernels_summary.txt)"}
+
         own_rays = rays_of(s1) - rays_of(s0)
-        achieved = own_rays * b_ray / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "k_extend (closest-hit traversal)", "achieved": achieved, "peak": peak,
-                    "peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
-                    "node_bytes": cs["node_bytes"], "prim_bytes": cs["prim_bytes"],
-                    "launches": ext_launches, "avg_launch_ms": ext_ms / max(ext_launches, 1),
-                    "share_of_step": ext_ms / max(s1["ms_render"] - s0["ms_render"], 1e-9),
-                    "note": "scene (BVH + triangles) largely L2-resident: algorithmic bytes are served by L2, achieved may exceed DRAM traffic"}
+        own_shadow = s1["rays_shadow_traced"] - s0["rays_shadow_traced"]
+        sh_ms = s1["ms_shadow"] - s0["ms_shadow"]
+        # closest hit: 32 B ray + 16 B hit; shadow: 32 B ray + 16 B contribution read + 16 B written
+        roofline = roof("k_traverse<closest> (extend rays)", "k_traverse_closest", rays_of(cs), cs["node_visits"], cs["prim_tests"], 48,
+                        own_rays, ext_ms, ext_launches)
+        roofline_shadow = roof("k_traverse<anyhit> (shadow rays)", "k_traverse_shadow", cs["rays_shadow_traced"], cs["node_visits_shadow"],
+                               cs["prim_tests_shadow"], 64, own_shadow, sh_ms, ext_launches)
         del cctx
 
     cpu_baseline = None
@@ -304,7 +320,8 @@ def main():
                 "spp_per_s": args.steps * SPP_PER_STEP / (dev_ms * 1e-3), "mshadow_per_s": shadow_all / (dev_ms * 1e3), "bvh_build_ms": build_ms,
                 "wall_ms_per_step": wall_ms / args.steps, "stage_ms": stage_ms,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 76 + 4, "d2h_bytes_per_step": int(d2h)},
-                "gather_bytes": tiles.bytes_on_the_wire(), "gather_ms": g0.elapsed_time(g1), "render_ms_rank0": s1["ms_render"] - s0["ms_render"], "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gather_bytes": tiles.bytes_on_the_wire(), "gather_ms": g0.elapsed_time(g1), "render_ms_rank0": s1["ms_render"] - s0["ms_render"], "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline_shadow if (roofline_shadow and roofline and roofline_shadow["share_of_step"] > roofline["share_of_step"]) else roofline,
+                "roofline_closest": roofline, "roofline_shadow": roofline_shadow, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

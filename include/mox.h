@@ -82,6 +82,9 @@ typedef struct mox_stats {
   double ms_generate, ms_extend, ms_shade, ms_shadow, ms_accumulate;
   uint64_t extend_launches;   /* closest-hit traversal kernel launches                   */
   uint64_t kernel_launches;   /* all kernels this library launched for launch/render     */
+  uint64_t node_visits_shadow; /* shadow-ray traversal, only with MOX_ACCEL_COUNTERS      */
+  uint64_t prim_tests_shadow;
+  uint64_t rays_shadow_traced; /* shadow rays with a non-zero contribution (the ones traversed) */
 } mox_stats;
 
 /* ---- context ------------------------------------------------------------- */

@@ -99,6 +99,7 @@ struct mox_ctx {
 
   // stats
   uint64_t raysPrimary = 0, raysBounce = 0, raysShadow = 0, nonfinite = 0, launches = 0, nodeVisits = 0, primTests = 0;
+  uint64_t nodeVisitsShadow = 0, primTestsShadow = 0, raysShadowTraced = 0;
   double msRender = 0, msBuild = 0;
   double msStage[ST_COUNT] = {0, 0, 0, 0, 0};
   uint64_t extendLaunches = 0, kernelLaunches = 0;
@@ -360,10 +361,11 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
       tm.end(c->stream);
       c->kernelLaunches += 2;
     }
-    CUCK(c, cudaMemcpyAsync(host, pb.counters, 4, cudaMemcpyDeviceToHost, c->stream));
-    CUCK(c, cudaMemsetAsync(pb.counters, 0, 8 * 4, c->stream));  // next count + material counts
+    CUCK(c, cudaMemcpyAsync(host, pb.counters, 8 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUCK(c, cudaMemsetAsync(pb.counters, 0, 8 * 4, c->stream));  // next count + material counts + shadow queue length
     CUCK(c, cudaStreamSynchronize(c->stream));
     count = host[C_NEXT];
+    c->raysShadowTraced += host[C_SHQ];
     if (c->sortRays && count > 4096) {
       // 24-bit keys -> 3 passes: the sorted queue lands in (kBuf[1], qBuf[iSpare])
       tm.begin(ST_SHADE, c->stream);
@@ -388,6 +390,8 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
   c->raysShadow += host[C_SHADOW];
   c->nodeVisits += ((uint64_t)host[C_NODEVIS_HI] << 32) | host[C_NODEVIS_LO];
   c->primTests += ((uint64_t)host[C_PRIMTEST_HI] << 32) | host[C_PRIMTEST_LO];
+  c->nodeVisitsShadow += ((uint64_t)host[C_NODEVIS_SH_LO + 1] << 32) | host[C_NODEVIS_SH_LO];
+  c->primTestsShadow += ((uint64_t)host[C_PRIMTEST_SH_LO + 1] << 32) | host[C_PRIMTEST_SH_LO];
   c->launches += S;
   return MOX_OK;
 }
@@ -723,6 +727,7 @@ int mox_clear_accum(mox_ctx* c) {
   if (c->dAccu) CUCK(c, cudaMemsetAsync(c->dAccu, 0, (size_t)c->accuW * c->accuH * 12, c->stream));
   CUCK(c, cudaStreamSynchronize(c->stream));
   c->launches = 0; c->raysPrimary = c->raysBounce = c->raysShadow = c->nonfinite = c->nodeVisits = c->primTests = 0;
+  c->nodeVisitsShadow = c->primTestsShadow = c->raysShadowTraced = 0;
   c->msRender = 0;
   for (double& m : c->msStage) m = 0;
   c->extendLaunches = c->kernelLaunches = 0;
@@ -805,6 +810,8 @@ int mox_get_stats(mox_ctx* c, mox_stats* s) {
   s->ms_generate = c->msStage[ST_GENERATE]; s->ms_extend = c->msStage[ST_EXTEND]; s->ms_shade = c->msStage[ST_SHADE];
   s->ms_shadow = c->msStage[ST_SHADOW]; s->ms_accumulate = c->msStage[ST_ACCUMULATE];
   s->extend_launches = c->extendLaunches; s->kernel_launches = c->kernelLaunches;
+  s->node_visits_shadow = c->nodeVisitsShadow; s->prim_tests_shadow = c->primTestsShadow;
+  s->rays_shadow_traced = c->raysShadowTraced;
   return MOX_OK;
 }
 

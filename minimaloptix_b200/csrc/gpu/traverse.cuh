@@ -234,8 +234,9 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
           MOX_ST_STREAM(job.hits + rayId, make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma));
         }
         if (COUNT) {
-          atomicAdd((unsigned long long*)(job.counters + 10), (unsigned long long)nv);
-          atomicAdd((unsigned long long*)(job.counters + 12), (unsigned long long)np);
+          // closest hit: words 10/12, shadow: 16/18 (CounterSlot in wavefront.h)
+          atomicAdd((unsigned long long*)(job.counters + (ANYHIT ? 16 : 10)), (unsigned long long)nv);
+          atomicAdd((unsigned long long*)(job.counters + (ANYHIT ? 18 : 12)), (unsigned long long)np);
         }
         active = false;
       }

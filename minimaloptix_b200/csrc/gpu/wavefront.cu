@@ -460,7 +460,9 @@ void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool
   TraceJob job = jobIn;
   job.fetchThreshold = fetchThreshold();
   cudaMemsetAsync(job.cursor, 0, 4, stream);
-  if (anyHit) {
+  if (anyHit && count) {
+    k_traverse<true, true><<<persistentGrid<true, true>(job.count), TRAV_TPB, 0, stream>>>(s, job);
+  } else if (anyHit) {
     k_traverse<true, false><<<persistentGrid<true, false>(job.count), TRAV_TPB, 0, stream>>>(s, job);
   } else if (count) {
     k_traverse<false, true><<<persistentGrid<false, true>(job.count), TRAV_TPB, 0, stream>>>(s, job);
@@ -509,7 +511,7 @@ void launchShadow(const LaunchCtx& c, uint32_t disneyCount) {
   job.rayO = c.pb.shO; job.rayD = c.pb.shD; job.queue = c.pb.shQueue; job.count = (uint32_t)slots;
   job.countPtr = c.pb.counters + C_SHQ; job.originMod = disneyCount;
   job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
-  launchTraverse(c.scene, job, true, false, c.stream);
+  launchTraverse(c.scene, job, true, c.countTraversal, c.stream);
 }
 void launchApply(const LaunchCtx& c, uint32_t disneyCount) {
   if (disneyCount && c.scene.nLights) k_apply<<<grid(disneyCount), TPB, 0, c.stream>>>(c, disneyCount);

@@ -11,7 +11,7 @@ enum ShadeQueue { Q_LAMBERT = 0, Q_METAL = 1, Q_DIELECTRIC = 2, Q_DISNEY = 3, Q_
 
 // Device counters (uint32 words).
 enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_SHQ = 5 /* shadow queue length */, C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
-                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_WORDS = 16 };
+                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_NODEVIS_SH_LO = 16, C_PRIMTEST_SH_LO = 18, C_WORDS = 20 };
 
 struct PathBuffers {
   size_t capacity = 0;      // paths

@@ -73,7 +73,7 @@ class Stats(C.Structure):
                 ("prim_bytes", C.c_uint32), ("n_lights", C.c_uint32),
                 ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double),
                 ("ms_shadow", C.c_double), ("ms_accumulate", C.c_double), ("extend_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("node_visits_shadow", C.c_uint64), ("prim_tests_shadow", C.c_uint64), ("rays_shadow_traced", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
