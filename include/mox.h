@@ -61,7 +61,8 @@ typedef enum mox_rng_mode { MOX_RNG_REF = 0, MOX_RNG_PHILOX = 1 } mox_rng_mode;
 /* mox_build_accel flags */
 #define MOX_ACCEL_DEFAULT 0u
 #define MOX_ACCEL_LBVH 1u        /* Karras radix tree instead of PLOC: fastest build, slower rays */
-#define MOX_ACCEL_COUNTERS 2u    /* traversal kernels count node visits / prim tests */
+#define MOX_ACCEL_COUNTERS 2u
+#define MOX_ACCEL_BINARY 4u      /* traverse the binary BVH, do not build the compressed 8-wide one */    /* traversal kernels count node visits / prim tests */
 
 typedef struct mox_stats {
   uint64_t rays_primary;      /* camera rays traced (closest hit)                 */

@@ -40,6 +40,7 @@ struct BuildInput {
   DeviceArena* arena = nullptr;  // required
   bool usePloc = true;   // false: Karras radix tree (fastest build, lower quality)
   int plocRadius = 16;
+  bool useWide = true;   // collapse the PLOC tree into the compressed 8-wide BVH
 };
 
 // Scratch of the PLOC hierarchy builder (ploc.cu), allocated before the timed build.
@@ -65,6 +66,10 @@ struct BuildOutput {
   int nNodes = 0;
   float4* packed = nullptr;   // 3 float4 per valid primitive in leaf order
   size_t nodesCap = 0, packedCap = 0;
+  BvhNode8* nodes8 = nullptr;  // compressed wide BVH (only when built from PLOC); same reuse rule
+  float4* packed8 = nullptr;   // primitives in wide-leaf order
+  size_t nodes8Cap = 0, packed8Cap = 0;
+  int nNodes8 = 0, wideLevels = 0;
   int nValid = 0, nInvalid = 0;
   int iterations = 0;
   bool usedPloc = false;  // false: Karras radix tree (requested, or PLOC fallback because of depth)
@@ -80,3 +85,8 @@ bool radixSortPairs(uint32_t* keys, uint32_t* vals, int n, cudaStream_t stream, 
 size_t radixSortScratchBytes(size_t maxN);
 void radixSortAsync(uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB, int n, int passes, uint32_t* scratch,
                     cudaStream_t stream);
+
+// Collapse of the PLOC tree into the compressed wide BVH (bvh_wide.cu).
+size_t wideScratchBytes(int n);
+bool wideCollapse(const PlocScratch& s, int n, uint32_t root, DeviceArena& arena, BvhNode8* outNodes, uint32_t** orderedIds8Out,
+                  int* nNodesOut, int* levelsOut, cudaStream_t stream, std::string& err);

@@ -373,6 +373,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   {  // keep the caller's reusable buffers, reset everything else
     BuildOutput fresh;
     fresh.nodes = out.nodes; fresh.packed = out.packed; fresh.nodesCap = out.nodesCap; fresh.packedCap = out.packedCap;
+    fresh.nodes8 = out.nodes8; fresh.packed8 = out.packed8; fresh.nodes8Cap = out.nodes8Cap; fresh.packed8Cap = out.packed8Cap;
     out = fresh;
   }
   DeviceArena& arena = *in.arena;
@@ -421,6 +422,8 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   const size_t nn = (size_t)n, ni = (size_t)nInnerMax;
   size_t scratchBytes = nn * (2 * 16 + 4 * 4 + 4) + smallWords * 4 + (size_t)4 * nTiles * 256 * 4 + ni * (8 + 8 + 4 + 16 + 16 + 4) + 20 * 256;
   if (in.usePloc && n >= 2) scratchBytes += plocScratchBytes(n);
+  const bool wantWide = in.usePloc && in.useWide && n >= 2;
+  if (wantWide) scratchBytes += wideScratchBytes(n);
   if (!arena.reserve(scratchBytes)) return bail("out of device memory (build scratch)");
   boxLo = arena.take<float4>(nn); boxHi = arena.take<float4>(nn);
   keysA = arena.take<uint32_t>(nn); keysB = arena.take<uint32_t>(nn);
@@ -433,6 +436,18 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   arrivals = arena.take<uint32_t>(ni);
   if (!arrivals) return bail("build arena too small");
   if (!ensureOut(ni, nn)) return bail("out of device memory (BVH)");
+  if (wantWide) {
+    if (out.nodes8Cap < nn || !out.nodes8) {
+      cudaFree(out.nodes8); out.nodes8 = nullptr; out.nodes8Cap = 0;
+      if (cudaMalloc(&out.nodes8, nn * sizeof(BvhNode8)) != cudaSuccess) return bail("out of device memory (wide BVH)");
+      out.nodes8Cap = nn;
+    }
+    if (out.packed8Cap < nn || !out.packed8) {
+      cudaFree(out.packed8); out.packed8 = nullptr; out.packed8Cap = 0;
+      if (cudaMalloc(&out.packed8, nn * 48) != cudaSuccess) return bail("out of device memory (wide BVH)");
+      out.packed8Cap = nn;
+    }
+  }
   out.scratchLo = boxLo; out.scratchHi = boxHi;
   if (in.usePloc && n >= 2) {
     std::string perr;
@@ -499,6 +514,12 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
     if (out.maxDepth <= MOX_TRAVERSAL_STACK - 2) {
     k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, out.packed);
+    if (wantWide) {
+      uint32_t* ordered8 = nullptr;
+      const uint32_t rootId = (uint32_t)(nValid + nValid - 2);  // the last node PLOC created
+      if (!wideCollapse(ploc, nValid, rootId, arena, out.nodes8, &ordered8, &out.nNodes8, &out.wideLevels, stream, perr)) return bail(perr);
+      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, out.packed8);
+    }
     if (in.evStop) CKB(cudaEventRecord(in.evStop, stream));
     CKB(cudaStreamSynchronize(stream));
     CKB(cudaGetLastError());

@@ -1,0 +1,195 @@
+// bvh_wide.cu — collapse of the binary PLOC tree into a compressed 8-wide BVH
+// (Ylitie, Karras, Laine 2017).  One thread per wide node, level by level:
+//   * start from the two children of a binary node and keep opening the child with the largest
+//     surface area until there are 8 children or nothing left to open; binary subtrees of
+//     <= MOX_WIDE_LEAF_MAX primitives become leaf children;
+//   * children are placed in the 8 slots by the octant of their centroid relative to the node
+//     centre (nearest free slot when taken), which is what lets traversal order them by
+//     slot ^ ray-octant;
+//   * child boxes are quantised to 8 bits per plane on a per-node power-of-two grid, rounded
+//     outwards and verified, so the wide BVH never culls what the binary one would keep;
+//   * inner children get consecutive node indices, the primitives of the leaf children a
+//     consecutive block of the wide-leaf-ordered primitive array (both via atomic counters).
+#include "build.h"
+#include "vec.cuh"
+
+namespace {
+
+struct WorkItem { uint32_t binNode; uint32_t wideIndex; };
+
+__device__ __forceinline__ float halfArea(const float4& lo, const float4& hi) {
+  float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// biased exponent e such that 255 * 2^(e-127) >= extent (and >= a tiny positive grid for flat boxes)
+__device__ __forceinline__ uint32_t gridExponent(float extent) {
+  float v = fmaxf(extent, 1e-30f) * (1.0f / 255.0f);
+  int k;
+  frexpf(v, &k);  // v = m * 2^k, m in [0.5, 1)  ->  2^k > v
+  int e = k + 127;
+  e = max(1, min(e, 254));
+  // guard against rounding in the division above
+  while (e < 254 && 255.0f * __uint_as_float((uint32_t)e << 23) < extent) ++e;
+  return (uint32_t)e;
+}
+
+__global__ void __launch_bounds__(128)
+k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, const uint2* __restrict__ children,
+                 const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi, const uint32_t* __restrict__ size,
+                 const uint32_t* __restrict__ parent, const uint32_t* __restrict__ leafPos, uint32_t root,
+                 const uint32_t* __restrict__ orderedIds, BvhNode8* __restrict__ out, uint32_t* __restrict__ orderedIds8,
+                 WorkItem* __restrict__ nextItems, uint32_t* __restrict__ counters /* [0] nodes, [1] prims, [2] next items */) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nItems) return;
+  const WorkItem it = items[w];
+  // ---- gather up to 8 children by repeatedly opening the largest openable one
+  uint32_t ch[8];
+  int n = 0;
+  {
+    uint2 c = children[it.binNode - nLeaves];
+    ch[n++] = c.x; ch[n++] = c.y;
+  }
+  while (n < 8) {
+    int best = -1;
+    float bestA = -1.f;
+    for (int i = 0; i < n; ++i) {
+      if (ch[i] < (uint32_t)nLeaves || size[ch[i]] <= MOX_WIDE_LEAF_MAX) continue;  // a leaf child stays closed
+      float a = halfArea(nodeLo[ch[i]], nodeHi[ch[i]]);
+      if (a > bestA) { bestA = a; best = i; }
+    }
+    if (best < 0) break;
+    uint2 c = children[ch[best] - nLeaves];
+    ch[best] = c.x;
+    ch[n++] = c.y;
+  }
+  // ---- node box and grid
+  const float4 blo = nodeLo[it.binNode], bhi = nodeHi[it.binNode];
+  const uint32_t ex = gridExponent(bhi.x - blo.x), ey = gridExponent(bhi.y - blo.y), ez = gridExponent(bhi.z - blo.z);
+  const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
+  const float cx = 0.5f * (blo.x + bhi.x), cy = 0.5f * (blo.y + bhi.y), cz = 0.5f * (blo.z + bhi.z);
+  // ---- slots by centroid octant, nearest free slot (Hamming distance) when taken
+  int slotOf[8];
+  uint32_t used = 0;
+  for (int i = 0; i < n; ++i) {
+    float4 lo = nodeLo[ch[i]], hi = nodeHi[ch[i]];
+    int want = ((0.5f * (lo.x + hi.x) > cx) ? 4 : 0) | ((0.5f * (lo.y + hi.y) > cy) ? 2 : 0) | ((0.5f * (lo.z + hi.z) > cz) ? 1 : 0);
+    int bestS = -1, bestD = 99;
+    for (int s = 0; s < 8; ++s) {
+      if (used & (1u << s)) continue;
+      int d = __popc((uint32_t)(s ^ want));
+      if (d < bestD) { bestD = d; bestS = s; }
+    }
+    slotOf[i] = bestS;
+    used |= 1u << bestS;
+  }
+  // ---- classify, count, allocate
+  uint32_t imask = 0, nInner = 0, nPrims = 0;
+  int childAt[8];
+  for (int s = 0; s < 8; ++s) childAt[s] = -1;
+  for (int i = 0; i < n; ++i) {
+    childAt[slotOf[i]] = i;
+    bool inner = ch[i] >= (uint32_t)nLeaves && size[ch[i]] > MOX_WIDE_LEAF_MAX;
+    if (inner) { imask |= 1u << slotOf[i]; nInner++; }
+    else nPrims += ch[i] < (uint32_t)nLeaves ? 1u : size[ch[i]];
+  }
+  const uint32_t childBase = nInner ? atomicAdd(&counters[0], nInner) : 0u;
+  const uint32_t primBase = nPrims ? atomicAdd(&counters[1], nPrims) : 0u;
+  const uint32_t nextBase = nInner ? atomicAdd(&counters[2], nInner) : 0u;
+  // ---- emit
+  uint32_t meta[8], qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
+  uint32_t innerRank = 0, primOff = 0;
+  for (int s = 0; s < 8; ++s) {
+    int i = childAt[s];
+    if (i < 0) {  // empty slot: inverted box, never hit
+      meta[s] = 0; qlx[s] = qly[s] = qlz[s] = 255; qhx[s] = qhy[s] = qhz[s] = 0;
+      continue;
+    }
+    const uint32_t c = ch[i];
+    const float4 lo = nodeLo[c], hi = nodeHi[c];
+    // outward rounding, then verify against the float planes the traversal will reconstruct
+    int ql, qh;
+    ql = (int)floorf((lo.x - blo.x) / sx); ql = max(0, min(255, ql)); while (ql > 0 && blo.x + ql * sx > lo.x) --ql;
+    qh = (int)ceilf((hi.x - blo.x) / sx); qh = max(0, min(255, qh)); while (qh < 255 && blo.x + qh * sx < hi.x) ++qh;
+    qlx[s] = ql; qhx[s] = qh;
+    ql = (int)floorf((lo.y - blo.y) / sy); ql = max(0, min(255, ql)); while (ql > 0 && blo.y + ql * sy > lo.y) --ql;
+    qh = (int)ceilf((hi.y - blo.y) / sy); qh = max(0, min(255, qh)); while (qh < 255 && blo.y + qh * sy < hi.y) ++qh;
+    qly[s] = ql; qhy[s] = qh;
+    ql = (int)floorf((lo.z - blo.z) / sz); ql = max(0, min(255, ql)); while (ql > 0 && blo.z + ql * sz > lo.z) --ql;
+    qh = (int)ceilf((hi.z - blo.z) / sz); qh = max(0, min(255, qh)); while (qh < 255 && blo.z + qh * sz < hi.z) ++qh;
+    qlz[s] = ql; qhz[s] = qh;
+    if (imask & (1u << s)) {
+      meta[s] = (1u << 5) | (24u + (uint32_t)s);
+      nextItems[nextBase + innerRank] = WorkItem{c, childBase + innerRank};
+      innerRank++;
+    } else {
+      uint32_t cnt = c < (uint32_t)nLeaves ? 1u : size[c];
+      // first primitive of the subtree in binary leaf order
+      uint32_t first;
+      if (c < (uint32_t)nLeaves) first = leafPos[c];
+      else {
+        uint32_t node = c, pos = 0;
+        while (node != root) { uint32_t p = parent[node]; uint2 pc = children[p - nLeaves]; if (pc.y == node) pos += size[pc.x]; node = p; }
+        first = pos;
+      }
+      for (uint32_t k = 0; k < cnt; ++k) orderedIds8[primBase + primOff + k] = orderedIds[first + k];
+      meta[s] = (((1u << cnt) - 1u) << 5) | primOff;
+      primOff += cnt;
+    }
+  }
+  auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+  BvhNode8 nd;
+  nd.n0 = make_float4(blo.x, blo.y, blo.z, __uint_as_float(ex | (ey << 8) | (ez << 16) | (imask << 24)));
+  nd.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
+  nd.n2 = make_float4(__uint_as_float(pack4(qlx)), __uint_as_float(pack4(qlx + 4)), __uint_as_float(pack4(qly)), __uint_as_float(pack4(qly + 4)));
+  nd.n3 = make_float4(__uint_as_float(pack4(qlz)), __uint_as_float(pack4(qlz + 4)), __uint_as_float(pack4(qhx)), __uint_as_float(pack4(qhx + 4)));
+  nd.n4 = make_float4(__uint_as_float(pack4(qhy)), __uint_as_float(pack4(qhy + 4)), __uint_as_float(pack4(qhz)), __uint_as_float(pack4(qhz + 4)));
+  out[it.wideIndex] = nd;
+}
+
+inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+#define WCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+size_t wideScratchBytes(int n) {
+  // two work queues of at most n/2 items (8 B each), 4 counters, the wide-leaf order; slack for alignment
+  return (size_t)std::max(n, 2) * (8 + 8 + 4) + 4 * 256 + 1024;
+}
+
+// Collapse the PLOC tree held in `s` (n >= 2 leaves) into outNodes (capacity >= n wide nodes) and
+// fill orderedIds8 (n entries).  *nNodesOut receives the number of wide nodes.
+bool wideCollapse(const PlocScratch& s, int n, uint32_t root, DeviceArena& arena, BvhNode8* outNodes, uint32_t** orderedIds8Out,
+                  int* nNodesOut, int* levelsOut, cudaStream_t stream, std::string& err) {
+  WorkItem* q[2] = {arena.take<WorkItem>((size_t)n), arena.take<WorkItem>((size_t)n)};
+  uint32_t* counters = arena.take<uint32_t>(4);
+  uint32_t* orderedIds8 = arena.take<uint32_t>((size_t)n);
+  if (!orderedIds8 || !q[0] || !q[1] || !counters) { err = "wide-BVH scratch does not fit the build arena"; return false; }
+  uint32_t init[4] = {1u, 0u, 0u, 0u};  // node 0 is the root
+  WorkItem rootItem{root, 0u};
+  WCK(cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, stream));
+  WCK(cudaMemcpyAsync(q[0], &rootItem, sizeof rootItem, cudaMemcpyHostToDevice, stream));
+  int cur = 0, count = 1, levels = 0;
+  while (count > 0) {
+    k_collapse_level<<<divUp(count, 128), 128, 0, stream>>>(count, q[cur], n, s.children, s.nodeLo, s.nodeHi, s.size, s.parent, s.leafPos,
+                                                           root, s.orderedIds, outNodes, orderedIds8, q[cur ^ 1], counters);
+    uint32_t host[4];
+    WCK(cudaMemcpyAsync(host, counters, sizeof host, cudaMemcpyDeviceToHost, stream));
+    WCK(cudaStreamSynchronize(stream));
+    count = (int)host[2];
+    uint32_t zero = 0;
+    WCK(cudaMemcpyAsync(counters + 2, &zero, 4, cudaMemcpyHostToDevice, stream));
+    cur ^= 1;
+    if (++levels > 4096) { err = "wide collapse did not terminate"; return false; }
+    *nNodesOut = (int)host[0];
+    if ((int)host[1] > n) { err = "wide collapse emitted too many primitives"; return false; }
+  }
+  uint32_t host[4];
+  WCK(cudaMemcpy(host, counters, sizeof host, cudaMemcpyDeviceToHost));
+  if ((int)host[1] != n) { err = "wide collapse lost primitives (" + std::to_string(host[1]) + " of " + std::to_string(n) + ")"; return false; }
+  WCK(cudaGetLastError());
+  *orderedIds8Out = orderedIds8;
+  *levelsOut = levels;
+  return true;
+}

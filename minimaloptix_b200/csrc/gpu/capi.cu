@@ -79,6 +79,11 @@ struct mox_ctx {
   BvhNode2* dNodes = nullptr;
   float4* dPacked = nullptr;
   size_t nodesCap = 0, packedCap = 0;
+  BvhNode8* dNodes8 = nullptr;
+  float4* dPacked8 = nullptr;
+  size_t nodes8Cap = 0, packed8Cap = 0;
+  int nNodes8 = 0;
+  bool wideBuilt = false, useWide = true;
   DeviceArena buildArena;
   int nNodes = 0, nValid = 0;
   bool built = false, lightsDirty = true;
@@ -235,6 +240,8 @@ SceneView sceneView(const mox_ctx* c) {
   SceneView s;
   s.nodes = c->dNodes;
   s.packed = c->dPacked;
+  s.nodes8 = (c->wideBuilt && c->useWide) ? c->dNodes8 : nullptr;
+  s.packed8 = c->dPacked8;
   s.analytic = (const Analytic*)c->dAnalytic.p;
   s.prims = (const PrimDesc*)c->dPrims.p;
   s.mats = (const GpuMaterial*)c->dMats.p;
@@ -478,7 +485,7 @@ void mox_destroy(mox_ctx* c) {
   freeTextures(c);
   c->dTexObjs.release();
   c->buildArena.release();
-  cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dAccu); cudaFree(c->dOwned);
+  cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dNodes8); cudaFree(c->dPacked8); cudaFree(c->dAccu); cudaFree(c->dOwned);
   freePaths(c->pb);
   if (c->pinned) cudaFreeHost(c->pinned);
   c->timer.release();
@@ -662,11 +669,17 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   in.usePloc = (flags & MOX_ACCEL_LBVH) == 0;
   if (const char* env = getenv("MOX_PLOC_RADIUS")) in.plocRadius = atoi(env);
   if (const char* env = getenv("MOX_FORCE_LBVH")) { if (atoi(env)) in.usePloc = false; }
+  c->useWide = (flags & MOX_ACCEL_BINARY) == 0;
+  if (const char* env = getenv("MOX_FORCE_BINARY")) { if (atoi(env)) c->useWide = false; }
+  in.useWide = c->useWide;
   BuildOutput out;
   out.nodes = c->dNodes; out.packed = c->dPacked; out.nodesCap = c->nodesCap; out.packedCap = c->packedCap;
+  out.nodes8 = c->dNodes8; out.packed8 = c->dPacked8; out.nodes8Cap = c->nodes8Cap; out.packed8Cap = c->packed8Cap;
   std::string err;
   bool okBuild = buildBvh(in, out, c->stream, err);
   c->dNodes = out.nodes; c->dPacked = out.packed; c->nodesCap = out.nodesCap; c->packedCap = out.packedCap;
+  c->dNodes8 = out.nodes8; c->dPacked8 = out.packed8; c->nodes8Cap = out.nodes8Cap; c->packed8Cap = out.packed8Cap;
+  c->nNodes8 = out.nNodes8; c->wideBuilt = okBuild && out.nNodes8 > 0;
   if (!okBuild) return fail(c, MOX_ERR_CUDA, "build_accel: " + err);
   CUCK(c, cudaEventSynchronize(c->ev1));
   float ms = 0;
@@ -805,7 +818,8 @@ int mox_get_stats(mox_ctx* c, mox_stats* s) {
   s->ms_render = c->msRender; s->ms_build = c->msBuild;
   s->n_prims = (uint32_t)c->prims.size(); s->n_triangles = (uint32_t)c->tris.size();
   s->n_spheres = c->nSpheres; s->n_quads = c->nQuads;
-  s->n_nodes = (uint32_t)c->nNodes; s->node_bytes = sizeof(BvhNode2); s->prim_bytes = 16 * MOX_PACKED_F4;
+  const bool wide = c->wideBuilt && c->useWide;
+  s->n_nodes = (uint32_t)(wide ? c->nNodes8 : c->nNodes); s->node_bytes = wide ? sizeof(BvhNode8) : sizeof(BvhNode2); s->prim_bytes = 16 * MOX_PACKED_F4;
   s->n_lights = (uint32_t)c->lights.size();
   s->ms_generate = c->msStage[ST_GENERATE]; s->ms_extend = c->msStage[ST_EXTEND]; s->ms_shade = c->msStage[ST_SHADE];
   s->ms_shadow = c->msStage[ST_SHADOW]; s->ms_accumulate = c->msStage[ST_ACCUMULATE];

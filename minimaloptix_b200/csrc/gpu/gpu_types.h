@@ -49,6 +49,22 @@ static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 // the radix tree when a PLOC tree would not fit.
 #define MOX_TRAVERSAL_STACK 128
 
+// Compressed 8-wide node (after Ylitie, Karras, Laine 2017), 80 bytes = 5 x float4, 16-byte aligned:
+//   n0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16 | imask << 24)   p: box minimum; e*: biased exponents of the
+//        per-axis grid scale 2^(e-127); imask bit s: the child in slot s is an inner node
+//   n1 = (childBase, primBase, meta[0..3], meta[4..7])
+//        inner children are stored contiguously from childBase in slot order; the primitives of all leaf
+//        children are contiguous from primBase in the wide-leaf-ordered packed array
+//        meta: 0 = empty; inner: 0b001 << 5 | (24 + slot); leaf: unary count (1..3) << 5 | offset from primBase
+//   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])      child boxes, 8 bit per plane:
+//   n3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])      lo = p + qlo * scale (rounded down),
+//   n4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])      hi = p + qhi * scale (rounded up)
+// Slots are assigned by octant of the child centroid so that (slot ^ octant-mask of the ray) orders
+// the children front to back without computing distances.
+struct __align__(16) BvhNode8 { float4 n0, n1, n2, n3, n4; };
+static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
+#define MOX_WIDE_LEAF_MAX 3
+
 // Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.
 //   triangle: (p0, idbits) (e0 = p1 - p0, -) (e1 = p0 - p2, -)
 //   analytic: (index into Analytic[] as int bits, -, -, idbits)
@@ -58,6 +74,8 @@ static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 struct SceneView {
   const BvhNode2* nodes;
   const float4* packed;
+  const BvhNode8* nodes8;   // compressed wide BVH (null: traverse the binary BVH)
+  const float4* packed8;    // primitives in wide-leaf order
   const Analytic* analytic;
   const PrimDesc* prims;
   const GpuMaterial* mats;

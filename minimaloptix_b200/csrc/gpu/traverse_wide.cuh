@@ -1,0 +1,193 @@
+// traverse_wide.cuh — persistent-thread traversal of the compressed 8-wide BVH (BvhNode8,
+// gpu_types.h).  Same contract as traverseWarpPersistent (traverse.cuh): identical primitive tests,
+// (t, id) lexicographic closest hit, order-independent shadow transmittance; only the hierarchy
+// walked differs, so results are bit-identical to the binary traversal.
+//
+// Per lane: a node group G = (childBase, hit bits 31..24 | imask 7..0) and a primitive group
+// T = (primBase, 24 hit bits), plus a stack of postponed node groups (Ylitie et al. 2017).  One
+// node step pops the front-most child of G (highest bit of slot ^ octant order), pushes the rest of
+// G, fetches the 80-byte node and tests its 8 quantised child boxes: one FMA per plane on a grid
+// local to the node, near/far planes picked per ray sign for four children at a time.  Warp phase
+// voting as in the binary kernel: a node step or one primitive test per iteration.
+#pragma once
+#include "traverse.cuh"
+
+#define MOX_WIDE_STACK MOX_TRAVERSAL_STACK
+
+MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const TraceJob& job) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned ltMask = (1u << lane) - 1u;
+  const uint32_t jobCount = job.countPtr ? __ldg(job.countPtr) : job.count;
+  uint2 stack[MOX_WIDE_STACK];
+  int sp = 0;
+  uint32_t gBase = 0, gBits = 0;  // node group
+  uint32_t tBase = 0, tBits = 0;  // primitive group
+  bool active = false, exhausted = false;
+  uint32_t rayId = 0, octinv = 0;
+  float3 o = mk3(0.f), d = mk3(0.f), idir = mk3(0.f);
+  float tmin = 0.f, tBest = 0.f, bBeta = 0.f, bGamma = 0.f;
+  int bPrim = -1;
+  float3 atten = mk3(1.f);
+  uint32_t nv = 0, np = 0;
+
+  while (true) {
+    // ---------------- refill idle lanes
+    if (!exhausted) {
+      unsigned idle = __ballot_sync(FULL, !active);
+      if (idle) {
+        const int leader = __ffs(idle) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(job.cursor, (uint32_t)__popc(idle));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          uint32_t i = base + __popc(idle & ltMask);
+          if (i < jobCount) {
+            rayId = job.queue ? MOX_LD_STREAM(job.queue + i) : i;
+            uint32_t oId = job.originMod ? rayId % job.originMod : rayId;
+            float4 ro = MOX_LD_STREAM(job.rayO + oId), rd = MOX_LD_STREAM(job.rayD + rayId);
+            if (!(ANYHIT && rd.w < 0.f)) {
+              RayPre r = prepRay(mk3(ro), mk3(rd), ro.w);
+              o = r.o; d = r.d; idir = r.idir; tmin = r.tmin;
+              octinv = 7u ^ ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
+              tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
+              atten = mk3(1.f);
+              sp = 0;
+              gBase = 0; gBits = 0x80000000u;  // root: one pending child, imask 0 -> node index 0
+              tBase = 0; tBits = 0;
+              active = true;
+              if (COUNT) { nv = 0; np = 0; }
+            }
+          }
+        }
+        if (base + __popc(idle) >= jobCount) exhausted = true;
+      }
+    }
+    if (!__any_sync(FULL, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---------------- traverse until too few lanes are busy
+    while (true) {
+      const bool isTri = active && tBits != 0u;
+      const bool isNode = active && !isTri && (gBits & 0xff000000u) != 0u;
+      const unsigned nm = __ballot_sync(FULL, isNode), tm = __ballot_sync(FULL, isTri);
+      const unsigned busy = nm | tm;
+      if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
+      if (__popc(nm) >= __popc(tm)) {
+        if (isNode) {
+          // ---- pop the front-most pending child of G
+          const uint32_t bit = 31u - (uint32_t)__clz(gBits & 0xff000000u);
+          const uint32_t imaskG = gBits & 0xffu;
+          gBits &= ~(1u << bit);
+          const uint32_t slot = (bit - 24u) ^ octinv;
+          const uint32_t nodeIdx = gBase + __popc(imaskG & ((1u << slot) - 1u));
+          if (gBits & 0xff000000u) stack[sp++] = make_uint2(gBase, gBits);
+          // ---- fetch and test the node
+          const BvhNode8* nd = s.nodes8 + nodeIdx;
+          const float4 n0 = __ldg(&nd->n0), n1 = __ldg(&nd->n1), n2 = __ldg(&nd->n2), n3 = __ldg(&nd->n3), n4 = __ldg(&nd->n4);
+          if (COUNT) nv++;
+          const uint32_t ew = __float_as_uint(n0.w);
+          const float iax = __uint_as_float((ew & 0xffu) << 23) * idir.x;
+          const float iay = __uint_as_float(((ew >> 8) & 0xffu) << 23) * idir.y;
+          const float iaz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * idir.z;
+          const float oax = (n0.x - o.x) * idir.x, oay = (n0.y - o.y) * idir.y, oaz = (n0.z - o.z) * idir.z;
+          // conservative: every axis gets its own rounding bound (2^-21 of the local origin term), folded
+          // into separate near / far addends so the per-child cost stays one FMA per plane; the far side
+          // is additionally widened by 1e-5 relative
+          const float ex_ = 4.76837158203125e-07f * fabsf(oax), ey_ = 4.76837158203125e-07f * fabsf(oay), ez_ = 4.76837158203125e-07f * fabsf(oaz);
+          const float onx = oax - ex_, ofx = oax + ex_, ony = oay - ey_, ofy = oay + ey_, onz = oaz - ez_, ofz = oaz + ez_;
+          uint32_t hitmask = 0;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+            const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
+            const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
+            const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
+            const uint32_t nx = idir.x < 0.f ? qhx : qlx, fx = idir.x < 0.f ? qlx : qhx;
+            const uint32_t ny = idir.y < 0.f ? qhy : qly, fy = idir.y < 0.f ? qly : qhy;
+            const uint32_t nz = idir.z < 0.f ? qhz : qlz, fz = idir.z < 0.f ? qlz : qhz;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float tnx = fmaf(byteToFloat(nx, i), iax, onx), tfx = fmaf(byteToFloat(fx, i), iax, ofx);
+              const float tny = fmaf(byteToFloat(ny, i), iay, ony), tfy = fmaf(byteToFloat(fy, i), iay, ofy);
+              const float tnz = fmaf(byteToFloat(nz, i), iaz, onz), tfz = fmaf(byteToFloat(fz, i), iaz, ofz);
+              const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+              const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tBest)) * 1.00001f;
+              const uint32_t m = (meta4 >> (8 * i)) & 0xffu;
+              if (tn <= tf && m != 0u) {
+                uint32_t shift = m & 31u;
+                if (shift >= 24u) shift = 24u + ((shift - 24u) ^ octinv);  // inner child: front-to-back priority
+                hitmask |= (m >> 5) << shift;
+              }
+            }
+          }
+          gBase = __float_as_uint(n1.x);
+          gBits = (hitmask & 0xff000000u) | (ew >> 24);
+          tBase = __float_as_uint(n1.y);
+          tBits = hitmask & 0x00ffffffu;
+        }
+      } else {
+        if (isTri) {
+          // ---- one primitive of the current group
+          const uint32_t k = 31u - (uint32_t)__clz(tBits);
+          tBits &= ~(1u << k);
+          const float4* rec = s.packed8 + (size_t)(tBase + k) * MOX_PACKED_F4;
+          const float4 r0 = __ldg(rec);
+          if (COUNT) np++;
+          const uint32_t idbits = __float_as_uint(r0.w);
+          const uint32_t type = idbits >> 30;
+          const int id = (int)(idbits & 0x3fffffffu);
+          float t = 0.f, be = 0.f, ga = 0.f;
+          bool hit;
+          if (type == PT_TRI) {
+            const float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+            hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+          } else {
+            const Analytic* an = s.analytic + __float_as_int(r0.x);
+            if (type == PT_SPHERE) {
+              hit = sphereTest(__ldg(&an->a), o, d, tmin, tBest, !ANYHIT && id < bPrim, t);
+            } else {
+              Analytic q;
+              q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
+              hit = quadTest(q, o, d, tmin, t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+            }
+          }
+          if (hit) {
+            if (ANYHIT) {
+              const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
+              if (__ldg(&m->kind) == MOX_MAT_DISNEY) {
+                if (__ldg((const int*)&m->dis.brdfType) == GLASS) atten *= mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
+                else { atten = mk3(0.f); tBits = 0u; gBits = 0u; sp = 0; }  // blocked: drop all pending work
+              }
+            } else {
+              tBest = t; bPrim = id; bBeta = be; bGamma = ga;
+            }
+          }
+        }
+      }
+      // ---- out of work in the current groups: resume a postponed node group, or finish the ray
+      if (active && tBits == 0u && (gBits & 0xff000000u) == 0u) {
+        if (sp > 0) {
+          const uint2 g = stack[--sp];
+          gBase = g.x; gBits = g.y;
+        } else {
+          if (ANYHIT) {
+            float4 c = MOX_LD_STREAM(job.shC + rayId);
+            MOX_ST_STREAM(job.shC + rayId, make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w));
+          } else {
+            MOX_ST_STREAM(job.hits + rayId, make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma));
+          }
+          if (COUNT) {
+            atomicAdd((unsigned long long*)(job.counters + (ANYHIT ? 16 : 10)), (unsigned long long)nv);
+            atomicAdd((unsigned long long*)(job.counters + (ANYHIT ? 18 : 12)), (unsigned long long)np);
+          }
+          active = false;
+        }
+      }
+    }
+  }
+}

@@ -20,6 +20,7 @@
 
 #include "shading.cuh"
 #include "traverse.cuh"
+#include "traverse_wide.cuh"
 
 namespace {
 
@@ -86,6 +87,14 @@ constexpr int TRAV_TPB = 128;
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(TRAV_TPB, MOX_TRAV_MINBLOCKS) k_traverse(SceneView s, TraceJob job) {
   traverseWarpPersistent<ANYHIT, COUNT>(s, job);
+}
+
+#ifndef MOX_WIDE_MINBLOCKS
+#define MOX_WIDE_MINBLOCKS 1
+#endif
+template <bool ANYHIT, bool COUNT>
+__global__ void __launch_bounds__(TRAV_TPB, MOX_WIDE_MINBLOCKS) k_traverse_wide(SceneView s, TraceJob job) {
+  traverseWidePersistent<ANYHIT, COUNT>(s, job);
 }
 
 // Consumes the closest-hit records of the current queue: miss (miss.cu:10-12), light
@@ -434,14 +443,12 @@ void launchGenerate(const LaunchCtx& c, uint32_t nSamples) {
   if (c.rp.rngMode == 0) k_generate<0><<<grid(n), TPB, 0, c.stream>>>(c, n);
   else k_generate<1><<<grid(n), TPB, 0, c.stream>>>(c, n);
 }
-template <bool ANYHIT, bool COUNT>
-static unsigned persistentGrid(uint32_t count) {
-  static int blocksPerSm = 0, numSms = 0;
+template <class K>
+static unsigned persistentGridFor(K kernel, uint32_t count, int& blocksPerSm) {
+  static int numSms = 0;
+  if (!numSms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev); }
   if (!blocksPerSm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, k_traverse<ANYHIT, COUNT>, TRAV_TPB, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, TRAV_TPB, 0);
     if (blocksPerSm < 1) blocksPerSm = 1;
   }
   unsigned full = (unsigned)(numSms * blocksPerSm);
@@ -455,20 +462,22 @@ static int fetchThreshold() {
   return t;
 }
 
+template <bool ANYHIT, bool COUNT>
+static void launchTraverseT(const SceneView& s, const TraceJob& job, cudaStream_t stream) {
+  static int bpsBinary = 0, bpsWide = 0;
+  if (s.nodes8) k_traverse_wide<ANYHIT, COUNT><<<persistentGridFor(k_traverse_wide<ANYHIT, COUNT>, job.count, bpsWide), TRAV_TPB, 0, stream>>>(s, job);
+  else k_traverse<ANYHIT, COUNT><<<persistentGridFor(k_traverse<ANYHIT, COUNT>, job.count, bpsBinary), TRAV_TPB, 0, stream>>>(s, job);
+}
+
 void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool count, cudaStream_t stream) {
   if (!jobIn.count) return;
   TraceJob job = jobIn;
   job.fetchThreshold = fetchThreshold();
   cudaMemsetAsync(job.cursor, 0, 4, stream);
-  if (anyHit && count) {
-    k_traverse<true, true><<<persistentGrid<true, true>(job.count), TRAV_TPB, 0, stream>>>(s, job);
-  } else if (anyHit) {
-    k_traverse<true, false><<<persistentGrid<true, false>(job.count), TRAV_TPB, 0, stream>>>(s, job);
-  } else if (count) {
-    k_traverse<false, true><<<persistentGrid<false, true>(job.count), TRAV_TPB, 0, stream>>>(s, job);
-  } else {
-    k_traverse<false, false><<<persistentGrid<false, false>(job.count), TRAV_TPB, 0, stream>>>(s, job);
-  }
+  if (anyHit && count) launchTraverseT<true, true>(s, job, stream);
+  else if (anyHit) launchTraverseT<true, false>(s, job, stream);
+  else if (count) launchTraverseT<false, true>(s, job, stream);
+  else launchTraverseT<false, false>(s, job, stream);
 }
 
 void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
