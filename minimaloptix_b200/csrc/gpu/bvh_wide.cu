@@ -63,6 +63,23 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
     ch[best] = c.x;
     ch[n++] = c.y;
   }
+#ifndef MOX_WIDE_NO_FILL
+  // free slots left: also open small leaf subtrees (largest first), so the bottom nodes give every
+  // primitive its own 8-bit box instead of leaving slots empty
+  while (n < 8) {
+    int best = -1;
+    float bestA = -1.f;
+    for (int i = 0; i < n; ++i) {
+      if (ch[i] < (uint32_t)nLeaves) continue;  // a single primitive
+      float a = halfArea(nodeLo[ch[i]], nodeHi[ch[i]]);
+      if (a > bestA) { bestA = a; best = i; }
+    }
+    if (best < 0) break;
+    uint2 c = children[ch[best] - nLeaves];
+    ch[best] = c.x;
+    ch[n++] = c.y;
+  }
+#endif
   // ---- node box and grid
   const float4 blo = nodeLo[it.binNode], bhi = nodeHi[it.binNode];
   const uint32_t ex = gridExponent(bhi.x - blo.x), ey = gridExponent(bhi.y - blo.y), ez = gridExponent(bhi.z - blo.z);

@@ -63,7 +63,9 @@ static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 // the children front to back without computing distances.
 struct __align__(16) BvhNode8 { float4 n0, n1, n2, n3, n4; };
 static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
-#define MOX_WIDE_LEAF_MAX 3
+#ifndef MOX_WIDE_LEAF_MAX
+#define MOX_WIDE_LEAF_MAX 2  // measured: 2 -> 1037, 1 -> 1036, 3 -> 1013 Mrays/s (binary BVH: 1029)
+#endif
 
 // Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.
 //   triangle: (p0, idbits) (e0 = p1 - p0, -) (e1 = p0 - p2, -)

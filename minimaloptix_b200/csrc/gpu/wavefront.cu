@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(TRAV_TPB, MOX_TRAV_MINBLOCKS) k_traverse(Scene
 }
 
 #ifndef MOX_WIDE_MINBLOCKS
-#define MOX_WIDE_MINBLOCKS 1
+#define MOX_WIDE_MINBLOCKS 10
 #endif
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(TRAV_TPB, MOX_WIDE_MINBLOCKS) k_traverse_wide(SceneView s, TraceJob job) {
