@@ -104,6 +104,11 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+            // four children at once: inner children (position field 24..31 = 0b11xxx) get their slot
+            // XOR-ed with the ray's octant mask, which orders them front to back
+            const uint32_t inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t pos4 = (meta4 ^ ((inner4 >> 4) * octinv)) & 0x1f1f1f1fu;
+            const uint32_t cnt4 = (meta4 >> 5) & 0x07070707u;
             const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
             const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
             const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
@@ -117,12 +122,9 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
               const float tnz = fmaf(byteToFloat(nz, i), iaz, onz), tfz = fmaf(byteToFloat(fz, i), iaz, ofz);
               const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
               const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tBest)) * 1.00001f;
-              const uint32_t m = (meta4 >> (8 * i)) & 0xffu;
-              if (tn <= tf && m != 0u) {
-                uint32_t shift = m & 31u;
-                if (shift >= 24u) shift = 24u + ((shift - 24u) ^ octinv);  // inner child: front-to-back priority
-                hitmask |= (m >> 5) << shift;
-              }
+              // branch-free: an empty slot has count bits 0 (and an inverted box)
+              const uint32_t bitsI = tn <= tf ? ((cnt4 >> (8 * i)) & 0xffu) : 0u;
+              hitmask |= bitsI << ((pos4 >> (8 * i)) & 0xffu);
             }
           }
           gBase = __float_as_uint(n1.x);
