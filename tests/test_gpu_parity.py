@@ -86,7 +86,7 @@ def test_closest_hit_cornell_open_front(host, api_tables, orc, gpu_backend):
     assert nbad <= 3
 
 
-@pytest.mark.parametrize("flags", [S.ACCEL_DEFAULT, S.ACCEL_LBVH], ids=["ploc", "lbvh"])
+@pytest.mark.parametrize("flags", [S.ACCEL_DEFAULT, S.ACCEL_BINARY, S.ACCEL_LBVH], ids=["wide", "binary-ploc", "binary-lbvh"])
 def test_closest_hit_interior_mesh(host, api_tables, orc, gpu_backend, flags):
     sc = host.Scene.builtin("interior", 60000)
     info = sc.info()
@@ -104,7 +104,7 @@ def test_closest_hit_interior_mesh(host, api_tables, orc, gpu_backend, flags):
     assert nbad <= 2
 
 
-@pytest.mark.parametrize("flags", [S.ACCEL_DEFAULT, S.ACCEL_LBVH], ids=["ploc", "lbvh"])
+@pytest.mark.parametrize("flags", [S.ACCEL_DEFAULT, S.ACCEL_BINARY, S.ACCEL_LBVH], ids=["wide", "binary-ploc", "binary-lbvh"])
 def test_closest_hit_soup(host, api_tables, orc, gpu_backend, flags):
     sc = host.Scene.builtin("soup", 200000, 7)
     o, g = both(host, api_tables, orc, gpu_backend, sc, 64, 64, 5, flags=flags)
@@ -117,8 +117,8 @@ def test_closest_hit_soup(host, api_tables, orc, gpu_backend, flags):
 def test_full_size_soup_two_builders_agree(host, api_tables, gpu_backend):
     """BASELINE config 5 at full size (10 M triangles, 2^22 incoherent rays): the oracle cannot
     finish this in seconds, so the check is a size-independent property — two different
-    hierarchies (PLOC and the Karras radix tree) over the same primitives must report the same
-    closest hit, bit for bit, for every ray; and re-tracing is idempotent."""
+    hierarchies (the compressed 8-wide BVH collapsed from PLOC, and the binary Karras radix tree)
+    over the same primitives must report the same closest hit, bit for bit, for every ray; and re-tracing is idempotent."""
     import torch
     sc = host.Scene.builtin("soup", 10_000_000)
     a, b = gpu_backend.context(0), gpu_backend.context(0)
@@ -270,6 +270,25 @@ def test_textured_disney_matches_oracle(host, api_tables, orc, gpu_backend):
         img = a / 8
         assert (img[..., 0] > 2 * img[..., 1] + 0.02).any() and (img[..., 1] > 2 * img[..., 0] + 0.02).any()
         assert rmse <= 2e-3 and within >= 0.995 and rel <= 5e-3
+
+
+def test_wide_and_binary_traversal_render_identically(host, api_tables, gpu_backend):
+    """The acceleration structure must not influence the image: 8-wide vs binary BVH, bit for bit
+    (including the order-independent shadow transmittance through GLASS)."""
+    sc = host.Scene.builtin("interior", 30000)
+    imgs = []
+    for flags in (S.ACCEL_DEFAULT, S.ACCEL_BINARY, S.ACCEL_LBVH):
+        g = gpu_backend.context(0)
+        sc.upload(api_tables.gpu, g, 160, 90, 5)
+        g.build_accel(flags)
+        g.render(3, 9)
+        st = g.stats()
+        imgs.append((g.read_accum(), st["rays_bounce"], st["rays_shadow"], st["node_bytes"]))
+    assert imgs[0][3] == 80 and imgs[1][3] == 64
+    assert imgs[0][1:3] == imgs[1][1:3] == imgs[2][1:3]
+    # GLASS attenuation is a product over hits in traversal order: allow last-bit differences only there
+    assert np.allclose(imgs[0][0], imgs[1][0], rtol=0, atol=1e-5) and np.allclose(imgs[0][0], imgs[2][0], rtol=0, atol=1e-5)
+    assert np.mean(imgs[0][0] == imgs[1][0]) > 0.999
 
 
 def test_render_matches_oracle_philox(host, api_tables, orc, gpu_backend):
