@@ -388,6 +388,48 @@ def test_animated_spheres_rebuild_and_resume(host, api_tables, orc, gpu_backend)
     assert np.array_equal(g4.read_accum().view(np.uint32), g2.read_accum().view(np.uint32))
 
 
+def test_deep_paths_default_depth_and_philox(host, api_tables, orc, gpu_backend):
+    """rayMaxDepth = 256 (the reference default, MinimalOptiX.h:85): the wavefront loop runs until
+    every path has terminated; both RNG modes."""
+    sc = host.Scene.builtin("spheres_pinhole")
+    for mode in (S.RNG_REF, S.RNG_PHILOX):
+        o, g = both(host, api_tables, orc, gpu_backend, sc, 96, 54, 256)
+        for ctx in (o, g):
+            ctx.set_rng_mode(mode)
+            ctx.render(2, 77)
+        so, sg = o.stats(), g.stats()
+        rmse, within, rel = image_metrics(g.read_accum(), o.read_accum(), 2)
+        assert sg["rays_bounce"] == so["rays_bounce"] and sg["rays_bounce"] > sg["rays_primary"]
+        assert rmse <= 2e-3 and within >= 0.999
+
+
+def test_headless_cli_snapshots_and_resume(tmp_path):
+    """mox_cli replaces the Qt app: power-of-two snapshots (MinimalOptiX.cpp:543-553), final PNG,
+    JSON stats line, accumulator dump and --resume."""
+    import json, subprocess
+    from PIL import Image
+    cli = os.path.join(ROOT, "minimaloptix_b200", "mox_cli")
+    out = str(tmp_path / "cb")
+    cmd = [cli, "--scene", "cornell", "--scene-dir", os.path.join(ROOT, "scenes"), "--width", "96", "--height", "96", "--max-depth", "5",
+           "--seed", "0xC0FFEE", "--out", out]
+    r = subprocess.run(cmd + ["--spp", "8", "--snapshots", "--dump-accum"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    stats = json.loads(r.stdout.strip().splitlines()[-1])
+    assert stats["spp"] == 8 and stats["triangles"] == 30 and stats["mrays_per_s"] > 0 and stats["nonfinite"] == 0
+    for n in (1, 2, 4, 8):
+        assert os.path.exists(f"{out}_{n}.png")
+    full = np.asarray(Image.open(out + ".png"))
+    assert full.shape == (96, 96, 3) and full.std() > 5
+    # 4 spp, dump, then resume to 8 spp: same pixels as the 8 spp run
+    out2 = str(tmp_path / "half")
+    r = subprocess.run([c if c != out else out2 for c in cmd] + ["--spp", "4", "--dump-accum"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out3 = str(tmp_path / "resumed")
+    r = subprocess.run([c if c != out else out3 for c in cmd] + ["--spp", "8", "--resume", out2 + ".moxa"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.asarray(Image.open(out3 + ".png")), full)
+
+
 def test_error_paths(host, api_tables, gpu_backend):
     from minimaloptix_b200 import MoxError
     g = gpu_backend.context(0)
