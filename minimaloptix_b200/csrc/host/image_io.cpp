@@ -2,6 +2,7 @@
 // (reference: MinimalOptiX::updateContent / saveCurrentFrame, MinimalOptiX.cpp:43-84; Qt's
 // QImage/QColor replaced by a dependency-free PNG/PPM writer).
 #include "image_io.h"
+#include "jpeg_decode.h"
 
 #include <cctype>
 #include <cmath>
@@ -304,6 +305,12 @@ bool readImageRgba(const std::string& path, int& w, int& h, std::vector<float>& 
   if (!readWhole(path, f)) { err = "cannot open " + path; return false; }
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
   if (f.size() > 8 && !memcmp(f.data(), sig, 8)) return readPng(f, w, h, texels, err);
+  if (f.size() > 3 && f[0] == 0xff && f[1] == 0xd8) {
+    std::vector<uint8_t> px;
+    if (!decodeJpeg(f.data(), f.size(), w, h, px, err)) { err += ": " + path; return false; }
+    toTexels(px, w, h, 3, nullptr, texels);
+    return true;
+  }
   if (f.size() > 2 && f[0] == 'P' && (f[1] == '6' || f[1] == '5' || f[1] == 'F' || f[1] == 'f')) {
     // netpbm header: magic, width, height, maxval (or scale for PFM), one whitespace, data
     size_t pos = 2;

@@ -227,6 +227,52 @@ def test_texture_image_decoding(host):
             host.read_image(os.path.join(tmp, "missing.png"))
 
 
+JPEG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg")
+JPEG_CASES = [c["name"] for c in json.load(open(os.path.join(JPEG_DIR, "index.json")))["cases"]]
+
+
+@pytest.mark.parametrize("name", JPEG_CASES)
+def test_jpeg_decoding_matches_libjpeg_bit_for_bit(host, name):
+    """Baseline / progressive / restart-interval / grey / 4:4:4, 4:2:2, 4:2:0 JPEGs decode to exactly the
+    pixels libjpeg gives QImage (fixtures: scripts/make_jpeg_golden.py; tolerance 0)."""
+    case = [c for c in json.load(open(os.path.join(JPEG_DIR, "index.json")))["cases"] if c["name"] == name][0]
+    w, h = case["width"], case["height"]
+    want = np.fromfile(os.path.join(JPEG_DIR, name + ".rgb"), dtype=np.uint8).reshape(h, w, 3)
+    got = host.read_image(os.path.join(JPEG_DIR, name + ".jpg"))
+    assert got.shape == (h, w, 4)
+    assert np.array_equal(got[::-1, :, :3], want.astype(np.float32) / 255.0)
+    assert (got[..., 3] == 1).all()
+
+
+def test_jpeg_damaged_files_fail_cleanly(host):
+    """Truncated or corrupted streams either decode (missing data reads as zero bits) or raise; they never
+    crash or read out of bounds."""
+    data = open(os.path.join(JPEG_DIR, "prog420_q70.jpg"), "rb").read()
+    base = open(os.path.join(JPEG_DIR, "rst420.jpg"), "rb").read()
+    rng = np.random.default_rng(11)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "x.jpg")
+        for src in (data, base):
+            for cut in (2, 3, 20, 100, len(src) // 2, len(src) - 3):
+                open(p, "wb").write(src[:cut])
+                try:
+                    host.read_image(p)
+                except Exception as e:
+                    assert "JPEG" in str(e) or "image format" in str(e)
+            for _ in range(40):
+                b = bytearray(src)
+                for k in rng.integers(2, len(b), size=4):
+                    b[k] = int(rng.integers(0, 256))
+                open(p, "wb").write(bytes(b))
+                try:
+                    host.read_image(p)
+                except Exception as e:
+                    assert "JPEG" in str(e) or "image" in str(e)
+        open(p, "wb").write(b"\xff\xd8\xff\xc3\x00\x0b\x08\x00\x08\x00\x08\x01\x01\x11\x00\xff\xd9")
+        with pytest.raises(Exception, match="unsupported JPEG process"):
+            host.read_image(p)
+
+
 def _textured_scene(tmp):
     """A unit quad mesh with uvs and a 4x4 checker texture, lit by one quad light."""
     from PIL import Image
