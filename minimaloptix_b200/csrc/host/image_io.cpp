@@ -4,6 +4,7 @@
 #include "image_io.h"
 #include "jpeg_decode.h"
 
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdlib>
@@ -252,6 +253,9 @@ void toTexels(const std::vector<uint8_t>& px, int w, int h, int ch, const uint8_
     }
 }
 
+// PNG as QImage (libpng) presents it to the reference's texel loop (MinimalOptiX.cpp:445-479): grey / RGB /
+// palette with or without alpha at 1, 2, 4, 8 or 16 bits, Adam7 interlacing; 16-bit samples keep their
+// high byte, low-depth grey is scaled to 0..255, alpha is ignored (the loop reads red/green/blue only).
 bool readPng(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& texels, std::string& err) {
   size_t pos = 8;
   int depth = 0, ctype = 0, interlace = 0;
@@ -259,7 +263,7 @@ bool readPng(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& 
   while (pos + 12 <= f.size()) {
     uint32_t len = be32(&f[pos]);
     const uint8_t* type = &f[pos + 4];
-    if (pos + 12 + len > f.size()) break;
+    if (pos + 12 + (size_t)len > f.size()) break;
     const uint8_t* body = &f[pos + 8];
     if (!memcmp(type, "IHDR", 4) && len >= 13) { w = (int)be32(body); h = (int)be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12]; }
     else if (!memcmp(type, "PLTE", 4)) palette.assign(body, body + len);
@@ -267,34 +271,65 @@ bool readPng(const std::vector<uint8_t>& f, int& w, int& h, std::vector<float>& 
     else if (!memcmp(type, "IEND", 4)) break;
     pos += 12 + len;
   }
-  if (w <= 0 || h <= 0 || depth != 8 || interlace != 0) { err = "unsupported PNG (need 8-bit, non-interlaced)"; return false; }
-  int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-  if (!ch || (ctype == 3 && palette.size() < 3) || idat.size() < 6) { err = "unsupported PNG colour type"; return false; }
+  const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  const bool depthOk = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                     : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8) : (depth == 8 || depth == 16);
+  if (w <= 0 || h <= 0 || (int64_t)w * h > ((int64_t)1 << 28) || !ch || !depthOk || interlace > 1) { err = "unsupported PNG header"; return false; }
+  if (ctype == 3) palette.resize(3 * 256, 0);
+  if (idat.size() < 6) { err = "corrupt PNG data"; return false; }
   std::vector<uint8_t> raw;
-  raw.reserve((size_t)h * (w * ch + 1));
   Inflater inf(idat.data() + 2, idat.size() - 2, raw);  // skip the zlib header; the Adler-32 trailer is ignored
-  if (!inf.run() || raw.size() < (size_t)h * ((size_t)w * ch + 1)) { err = "corrupt PNG data"; return false; }
-  const size_t stride = (size_t)w * ch;
-  std::vector<uint8_t> px(stride * h);
-  for (int y = 0; y < h; ++y) {
-    const uint8_t* src = &raw[(size_t)y * (stride + 1)];
-    uint8_t* cur = &px[(size_t)y * stride];
-    const uint8_t* up = y ? cur - stride : nullptr;
-    int ft = src[0];
-    for (size_t i = 0; i < stride; ++i) {
-      int a = i >= (size_t)ch ? cur[i - ch] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)ch) ? up[i - ch] : 0;
-      int v = src[1 + i];
-      switch (ft) {
-        case 1: v += a; break;
-        case 2: v += b; break;
-        case 3: v += (a + b) >> 1; break;
-        case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
-        default: break;
+  const bool inflated = inf.run();
+  const int bpp = depth * ch;                    // bits per pixel
+  const size_t fu = (size_t)std::max(1, bpp / 8);  // filter unit in bytes
+  std::vector<uint8_t> px((size_t)w * h * 3);
+  std::vector<uint8_t> prev, cur;
+  size_t rp = 0;
+  // Adam7: pass p covers pixels (x0 + i*dx, y0 + j*dy); a non-interlaced image is one pass with unit steps
+  static const int X0[7] = {0, 4, 0, 2, 0, 1, 0}, Y0[7] = {0, 0, 4, 0, 2, 0, 1}, DX[7] = {8, 8, 4, 4, 2, 2, 1}, DY[7] = {8, 8, 8, 4, 4, 2, 2};
+  const int npass = interlace ? 7 : 1;
+  for (int p = 0; p < npass; ++p) {
+    const int x0 = interlace ? X0[p] : 0, y0 = interlace ? Y0[p] : 0, dx = interlace ? DX[p] : 1, dy = interlace ? DY[p] : 1;
+    const int pw = (w - x0 + dx - 1) / dx, ph = (h - y0 + dy - 1) / dy;
+    if (pw <= 0 || ph <= 0) continue;
+    const size_t stride = ((size_t)pw * bpp + 7) / 8;
+    prev.assign(stride, 0);
+    cur.resize(stride);
+    for (int j = 0; j < ph; ++j) {
+      if (rp + 1 + stride > raw.size()) { err = inflated ? "truncated PNG data" : "corrupt PNG data"; return false; }
+      const int ft = raw[rp];
+      const uint8_t* src = &raw[rp + 1];
+      rp += 1 + stride;
+      for (size_t i = 0; i < stride; ++i) {
+        const int a = i >= fu ? cur[i - fu] : 0, b = prev[i], c = i >= fu ? prev[i - fu] : 0;
+        int v = src[i];
+        switch (ft) {
+          case 1: v += a; break;
+          case 2: v += b; break;
+          case 3: v += (a + b) >> 1; break;
+          case 4: { int q = a + b - c, pa = abs(q - a), pb = abs(q - b), pc = abs(q - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+          default: break;
+        }
+        cur[i] = (uint8_t)v;
       }
-      cur[i] = (uint8_t)v;
+      const int y = y0 + j * dy;
+      for (int i = 0; i < pw; ++i) {
+        uint8_t s[4] = {0, 0, 0, 0};
+        if (depth == 8) for (int k = 0; k < ch; ++k) s[k] = cur[(size_t)i * ch + k];
+        else if (depth == 16) for (int k = 0; k < ch; ++k) s[k] = cur[((size_t)i * ch + k) * 2];
+        else {
+          const int bit = i * depth, v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+          s[0] = ctype == 3 ? (uint8_t)v : (uint8_t)(v * 255 / ((1 << depth) - 1));
+        }
+        uint8_t* d = &px[((size_t)y * w + x0 + i * dx) * 3];
+        if (ctype == 3) { const uint8_t* q = &palette[3 * s[0]]; d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; }
+        else if (ch <= 2) d[0] = d[1] = d[2] = s[0];
+        else { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+      }
+      prev.swap(cur);
     }
   }
-  toTexels(px, w, h, ch, ctype == 3 ? palette.data() : nullptr, texels);
+  toTexels(px, w, h, 3, nullptr, texels);
   return true;
 }
 

@@ -227,6 +227,86 @@ def test_texture_image_decoding(host):
             host.read_image(os.path.join(tmp, "missing.png"))
 
 
+def _write_png(path, samples, depth, ctype, interlace=False, palette=None):
+    """Minimal PNG writer for the decoder tests: `samples` is (h, w, channels) of integers < 2**depth."""
+    import zlib
+    h, w, ch = samples.shape
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xffffffff)
+
+    def rows(sub):
+        out = bytearray()
+        for r in sub:
+            flat = r.reshape(-1)
+            if depth == 16:
+                line = flat.astype(">u2").tobytes()
+            elif depth == 8:
+                line = flat.astype(np.uint8).tobytes()
+            else:
+                bits = np.zeros(((len(flat) * depth + 7) // 8) * 8, dtype=np.uint8)
+                for k in range(depth):
+                    bits[k:len(flat) * depth:depth] = (flat >> (depth - 1 - k)) & 1
+                line = np.packbits(bits).tobytes()
+            out += bytes([0]) + line
+        return bytes(out)
+
+    if interlace:
+        x0, y0, dx, dy = [0, 4, 0, 2, 0, 1, 0], [0, 0, 4, 0, 2, 0, 1], [8, 8, 4, 4, 2, 2, 1], [8, 8, 8, 4, 4, 2, 2]
+        raw = b"".join(rows(samples[y0[p]::dy[p], x0[p]::dx[p]]) for p in range(7)
+                       if samples[y0[p]::dy[p], x0[p]::dx[p]].size)
+    else:
+        raw = rows(samples)
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        data += chunk(b"PLTE", np.asarray(palette, dtype=np.uint8).tobytes())
+    data += chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
+    open(path, "wb").write(data)
+
+
+def test_png_depths_and_interlacing(host):
+    """1/2/4-bit grey and palette, 16-bit grey / RGB / RGBA (high byte kept), grey+alpha, Adam7 interlacing at
+    sizes that leave some passes empty — checked against the definition and against Pillow's decoder."""
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "t.png")
+        for (w, h) in ((1, 1), (3, 2), (9, 5), (33, 18)):
+            for interlace in (False, True):
+                for depth in (1, 2, 4, 8, 16):
+                    g = rng.integers(0, 2 ** depth, size=(h, w, 1))
+                    _write_png(p, g, depth, 0, interlace)
+                    want = (g >> 8 if depth == 16 else g * 255 // (2 ** depth - 1)).astype(np.float32) / 255.0
+                    got = host.read_image(p)
+                    assert np.array_equal(got[::-1, :, :3], np.repeat(want, 3, axis=2)), (w, h, interlace, depth)
+                    if depth <= 8:
+                        pil = np.asarray(Image.open(p).convert("RGB"), dtype=np.float32) / 255.0
+                        assert np.array_equal(got[::-1, :, :3], pil), ("pil", w, h, interlace, depth)
+                for depth in (1, 2, 4, 8):
+                    pal = rng.integers(0, 256, size=(2 ** depth, 3))
+                    idx = rng.integers(0, 2 ** depth, size=(h, w, 1))
+                    _write_png(p, idx, depth, 3, interlace, palette=pal)
+                    got = host.read_image(p)
+                    assert np.array_equal(got[::-1, :, :3], pal[idx[..., 0]].astype(np.float32) / 255.0), (w, h, interlace, depth)
+                    pil = np.asarray(Image.open(p).convert("RGB"), dtype=np.float32) / 255.0
+                    assert np.array_equal(got[::-1, :, :3], pil)
+                for ctype, ch in ((2, 3), (6, 4), (4, 2)):
+                    for depth in (8, 16):
+                        v = rng.integers(0, 2 ** depth, size=(h, w, ch))
+                        _write_png(p, v, depth, ctype, interlace)
+                        hi = (v >> 8 if depth == 16 else v).astype(np.float32) / 255.0
+                        want = hi[..., :3] if ch >= 3 else np.repeat(hi[..., :1], 3, axis=2)
+                        got = host.read_image(p)
+                        assert np.array_equal(got[::-1, :, :3], want), (w, h, interlace, ctype, depth)
+                        assert (got[..., 3] == 1).all()
+        # damaged streams fail with a message
+        _write_png(p, rng.integers(0, 256, size=(8, 8, 3)), 8, 2)
+        data = open(p, "rb").read()
+        open(p, "wb").write(data[:60])
+        with pytest.raises(Exception, match="PNG"):
+            host.read_image(p)
+
+
 JPEG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg")
 JPEG_CASES = [c["name"] for c in json.load(open(os.path.join(JPEG_DIR, "index.json")))["cases"]]
 
