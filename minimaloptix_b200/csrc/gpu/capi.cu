@@ -73,7 +73,8 @@ struct mox_ctx {
   uint32_t nSpheres = 0, nQuads = 0;
 
   // device scene
-  DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights;
+  DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights, dShadeRec;
+  bool shadeRecBuilt = false;
   DevBuf dQueryO, dQueryD, dQueryCounters;  // raw ray queries
   DevBuf dTexObjs;
   BvhNode2* dNodes = nullptr;
@@ -249,6 +250,7 @@ SceneView sceneView(const mox_ctx* c) {
   s.normals = (const float*)c->dNormals.p;
   s.uvs = (const float*)c->dUvs.p;
   s.tris = (const TriIdx*)c->dTris.p;
+  s.shadeRec = c->shadeRecBuilt ? (const float4*)c->dShadeRec.p : nullptr;
   s.lights = (const LightParams*)c->dLights.p;
   s.textures = (const cudaTextureObject_t*)c->dTexObjs.p;
   s.nLights = (int)c->lights.size();
@@ -479,7 +481,7 @@ void mox_destroy(mox_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dQueryO,
+  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dShadeRec, &c->dQueryO,
                    &c->dQueryD, &c->dQueryCounters}) b->release();
   for (auto& b : c->otherOwned) b.release();
   freeTextures(c);
@@ -653,6 +655,17 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   if ((rc = upload(c, c->dUvs, c->uvs))) return rc;
   if ((rc = upload(c, c->dAnalytic, c->analytic))) return rc;
   if ((rc = upload(c, c->dMats, c->mats))) return rc;
+  c->shadeRecBuilt = false;
+  {
+    bool want = !c->tris.empty();
+    if (const char* env = getenv("MOX_SHADE_RECORDS")) want = want && atoi(env) != 0;
+    if (want) {
+      if ((rc = ensure(c, c->dShadeRec, c->tris.size() * MOX_SHADE_REC_F4 * sizeof(float4)))) return rc;
+      launchBuildShadeRecords((const TriIdx*)c->dTris.p, (const float*)c->dVerts.p, (const float*)c->dNormals.p, (const float*)c->dUvs.p,
+                              (uint32_t)c->tris.size(), (float4*)c->dShadeRec.p, c->stream);
+      c->shadeRecBuilt = true;
+    }
+  }
   if ((rc = syncLights(c))) return rc;
   if ((rc = syncTextures(c))) return rc;
   for (auto& m : c->mats)

@@ -73,6 +73,11 @@ static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
 // idbits = prim id | type << 30.
 #define MOX_PACKED_F4 3
 
+// Per-triangle shading record, 128 bytes, indexed like `tris`:
+//   r0 = p0.xyz | flags (bit 0: has normals, bit 1: has uvs)     r1 = p1.xyz | uv0.x     r2 = p2.xyz | uv0.y
+//   r3 = n0.xyz | uv1.x     r4 = n1.xyz | uv1.y     r5 = n2.xyz | uv2.x     r6 = uv2.y, -, -, -     r7 unused
+#define MOX_SHADE_REC_F4 8
+
 struct SceneView {
   const BvhNode2* nodes;
   const float4* packed;
@@ -85,6 +90,7 @@ struct SceneView {
   const float* normals;  // xyz
   const float* uvs;      // uv
   const TriIdx* tris;
+  const float4* shadeRec;   // MOX_SHADE_REC_F4 float4 per triangle: what a hit needs for shading, pre-gathered (null: gather through tris)
   const LightParams* lights;
   const cudaTextureObject_t* textures;  // id - 1 -> float4 texture, bilinear, REPEAT, normalized coords
   int nLights;

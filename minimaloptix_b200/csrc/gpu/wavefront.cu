@@ -162,6 +162,27 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
     a.Ng = mk3(__ldg(&s.analytic[pd.geom].a));
     a.Ns = a.Ng;
     a.front = a.back = a.hitPoint;
+  } else if (s.shadeRec) {
+    const float4* r = s.shadeRec + (size_t)pd.geom * MOX_SHADE_REC_F4;
+    const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+    const float3 p0 = mk3(r0), p1 = mk3(r1), p2 = mk3(r2);
+    float3 e0 = p1 - p0, e1 = p0 - p2;
+    a.Ng = normalize(cross(e1, e0));
+    a.Ns = a.Ng;
+    a.front = a.back = a.hitPoint;
+    if (needShading) {
+      const uint32_t flags = __float_as_uint(r0.w);
+      if (flags) {
+        const float4 r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
+        if (flags & 1u) a.Ns = normalize(mk3(r4) * beta + mk3(r5) * gamma + mk3(r3) * (1.f - beta - gamma));
+        if (flags & 2u) {
+          float w = 1.0f - beta - gamma;
+          a.u = r3.w * beta + r5.w * gamma + r1.w * w;
+          a.v = r4.w * beta + __ldg(&r[6].x) * gamma + r2.w * w;
+        }
+      }
+      refineHitpoint(a.hitPoint, d, a.Ng, p0, a.back, a.front);
+    }
   } else {
     const TriIdx* ti = s.tris + pd.geom;
     int v0 = __ldg(&ti->v[0]), v1 = __ldg(&ti->v[1]), v2 = __ldg(&ti->v[2]);
@@ -402,6 +423,31 @@ __global__ void __launch_bounds__(TPB) k_accumulate(LaunchCtx c, uint32_t nSampl
 
 // ------------------------------------------------------------------ raw ray queries
 // out[i] = transmittance (the shC buffer is pre-set to 1)
+// scene upload: gathers each triangle's vertices, normals and uvs into one 128-byte record (gpu_types.h)
+__global__ void k_build_shade_records(const TriIdx* __restrict__ tris, const float* __restrict__ verts, const float* __restrict__ normals,
+                                      const float* __restrict__ uvs, uint32_t n, float4* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const TriIdx t = tris[i];
+  const bool hasN = t.n[0] >= 0, hasT = t.t[0] >= 0;
+  float3 p[3], nn[3];
+  float2 uv[3];
+  for (int k = 0; k < 3; ++k) {
+    p[k] = ld3(verts, t.v[k]);
+    nn[k] = hasN ? ld3(normals, t.n[k]) : mk3(0.f);
+    uv[k] = hasT ? make_float2(uvs[2 * t.t[k]], uvs[2 * t.t[k] + 1]) : make_float2(0.f, 0.f);
+  }
+  float4* r = out + (size_t)i * MOX_SHADE_REC_F4;
+  r[0] = make_float4(p[0].x, p[0].y, p[0].z, __uint_as_float((hasN ? 1u : 0u) | (hasT ? 2u : 0u)));
+  r[1] = make_float4(p[1].x, p[1].y, p[1].z, uv[0].x);
+  r[2] = make_float4(p[2].x, p[2].y, p[2].z, uv[0].y);
+  r[3] = make_float4(nn[0].x, nn[0].y, nn[0].z, uv[1].x);
+  r[4] = make_float4(nn[1].x, nn[1].y, nn[1].z, uv[1].y);
+  r[5] = make_float4(nn[2].x, nn[2].y, nn[2].z, uv[2].x);
+  r[6] = make_float4(uv[2].y, 0.f, 0.f, 0.f);
+  r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void k_fill_ones(float4* __restrict__ p, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = make_float4(1.f, 1.f, 1.f, 0.f);
@@ -530,6 +576,10 @@ void launchAccumulate(const LaunchCtx& c, uint32_t nSamples) {
 }
 void launchSplitRays(const float4* rays, float4* o, float4* d, size_t n, cudaStream_t stream) {
   if (n) k_split_rays<<<grid(n), TPB, 0, stream>>>(rays, o, d, n);
+}
+void launchBuildShadeRecords(const TriIdx* tris, const float* verts, const float* normals, const float* uvs, uint32_t n, float4* out,
+                             cudaStream_t stream) {
+  if (n) k_build_shade_records<<<(n + 255) / 256, 256, 0, stream>>>(tris, verts, normals, uvs, n, out);
 }
 void launchFillOnes(float4* p, size_t n, cudaStream_t stream) {
   if (n) k_fill_ones<<<grid(n), TPB, 0, stream>>>(p, n);

@@ -53,6 +53,8 @@ void launchAccumulate(const LaunchCtx& c, uint32_t nSamples);
 // Persistent traversal over one batch of rays (closest hit or shadow transmittance).
 void launchTraverse(const SceneView& s, const TraceJob& job, bool anyHit, bool count, cudaStream_t stream);
 void launchSplitRays(const float4* rays, float4* o, float4* d, size_t n, cudaStream_t stream);
+void launchBuildShadeRecords(const TriIdx* tris, const float* verts, const float* normals, const float* uvs, uint32_t n, float4* out,
+                             cudaStream_t stream);
 void launchFillOnes(float4* p, size_t n, cudaStream_t stream);
 void launchCopyRgb(const float4* src, float* dst, size_t n, cudaStream_t stream);
 void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream);
