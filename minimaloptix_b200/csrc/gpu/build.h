@@ -36,6 +36,7 @@ struct BuildInput {
   const TriIdx* tris = nullptr;        // device
   const float* verts = nullptr;        // device
   const Analytic* analytic = nullptr;  // device
+  const GpuMaterial* mats = nullptr;   // device: the packed records carry each primitive's shadow-ray class
   cudaEvent_t evStart = nullptr, evStop = nullptr;  // recorded around the build kernels when set
   DeviceArena* arena = nullptr;  // required
   bool usePloc = true;   // false: Karras radix tree (fastest build, lower quality)

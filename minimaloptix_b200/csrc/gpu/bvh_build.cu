@@ -338,13 +338,20 @@ __global__ void k_emit2(int n, const uint32_t* __restrict__ sortedIds, const flo
 }
 
 __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const PrimDesc* __restrict__ prims,
-                       const TriIdx* __restrict__ tris, const float* __restrict__ verts, float4* __restrict__ packed) {
+                       const TriIdx* __restrict__ tris, const float* __restrict__ verts, const GpuMaterial* __restrict__ mats,
+                       float4* __restrict__ packed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t id = sortedIds[i];
   PrimDesc pd = prims[id];
   uint32_t type = pd.typeMat & 3u;
   uint32_t idbits = id | (type << 30);
+  uint32_t shadowClass = MOX_SHADOW_INVISIBLE;
+  if (mats) {
+    const GpuMaterial* m = mats + (pd.typeMat >> 2);
+    if (m->kind == MOX_MAT_DISNEY) shadowClass = m->dis.brdfType == GLASS ? MOX_SHADOW_TINTS : MOX_SHADOW_BLOCKS;
+  }
+  const float sc = __uint_as_float(shadowClass);
   float4* rec = packed + (size_t)i * MOX_PACKED_F4;
   if (type == PT_TRI) {
     TriIdx t = tris[pd.geom];
@@ -353,11 +360,11 @@ __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const Prim
     float3 p2 = mk3(verts[3 * t.v[2]], verts[3 * t.v[2] + 1], verts[3 * t.v[2] + 2]);
     float3 e0 = p1 - p0, e1 = p0 - p2;
     rec[0] = make_float4(p0.x, p0.y, p0.z, __uint_as_float(idbits));
-    rec[1] = make_float4(e0.x, e0.y, e0.z, 0.f);
+    rec[1] = make_float4(e0.x, e0.y, e0.z, sc);
     rec[2] = make_float4(e1.x, e1.y, e1.z, 0.f);
   } else {
     rec[0] = make_float4(__int_as_float((int)pd.geom), 0.f, 0.f, __uint_as_float(idbits));
-    rec[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[1] = make_float4(0.f, 0.f, 0.f, sc);
     rec[2] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
@@ -482,7 +489,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out.nInvalid = (int)hostSmall[6];
 
   if (nValid > 0 && (nValid <= 1 || !in.usePloc))
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.mats, out.packed);
   if (nValid <= 1) {
     BvhNode2 root;
     root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);
@@ -513,12 +520,12 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     std::string perr;
     if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
     if (out.maxDepth <= MOX_TRAVERSAL_STACK - 2) {
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, in.mats, out.packed);
     if (wantWide) {
       uint32_t* ordered8 = nullptr;
       const uint32_t rootId = (uint32_t)(nValid + nValid - 2);  // the last node PLOC created
       if (!wideCollapse(ploc, nValid, rootId, arena, out.nodes8, &ordered8, &out.nNodes8, &out.wideLevels, stream, perr)) return bail(perr);
-      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, out.packed8);
+      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, in.mats, out.packed8);
     }
     if (in.evStop) CKB(cudaEventRecord(in.evStop, stream));
     CKB(cudaStreamSynchronize(stream));
@@ -528,7 +535,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     return true;
     }
     // too deep for the traversal stack: fall through to the radix tree (depth <= 62)
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.mats, out.packed);
   }
   k_karras<<<divUp(nInner, B), B, 0, stream>>>(nValid, kin, children, range, parentInternal, parentLeaf);
   k_refit<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, boxLo, boxHi, children, parentInternal, parentLeaf, nodeLo, nodeHi, arrivals);

@@ -678,6 +678,7 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   in.tris = (const TriIdx*)c->dTris.p;
   in.verts = (const float*)c->dVerts.p;
   in.analytic = (const Analytic*)c->dAnalytic.p;
+  in.mats = (const GpuMaterial*)c->dMats.p;
   in.evStart = c->ev0; in.evStop = c->ev1;
   in.usePloc = (flags & MOX_ACCEL_LBVH) == 0;
   if (const char* env = getenv("MOX_PLOC_RADIUS")) in.plocRadius = atoi(env);

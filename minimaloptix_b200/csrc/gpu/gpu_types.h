@@ -73,6 +73,12 @@ static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
 // idbits = prim id | type << 30.
 #define MOX_PACKED_F4 3
 
+// How a primitive answers a shadow ray (the order-independent any-hit rule, Material.cu:225-232): stored in
+// word 1 .w of its packed record so an occluded shadow ray needs no material lookup.
+#define MOX_SHADOW_INVISIBLE 0u  // no any-hit program (lambertian, metal, glass, light)
+#define MOX_SHADOW_BLOCKS 1u     // Disney NORMAL
+#define MOX_SHADOW_TINTS 2u      // Disney GLASS: attenuation *= color
+
 // Per-triangle shading record, 128 bytes, indexed like `tris`:
 //   r0 = p0.xyz | flags (bit 0: has normals, bit 1: has uvs)     r1 = p1.xyz | uv0.x     r2 = p2.xyz | uv0.y
 //   r3 = n0.xyz | uv1.x     r4 = n1.xyz | uv1.y     r5 = n2.xyz | uv2.x     r6 = uv2.y, -, -, -     r7 unused

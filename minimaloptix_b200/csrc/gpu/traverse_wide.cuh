@@ -138,20 +138,21 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           const uint32_t k = 31u - (uint32_t)__clz(tBits);
           tBits &= ~(1u << k);
           const float4* rec = s.packed8 + (size_t)(tBase + k) * MOX_PACKED_F4;
-          const float4 r0 = __ldg(rec);
+          // All three words are fetched and the triangle test runs before the type tag is looked at (for the
+          // rare analytic slot its result is discarded): waiting for the tag first would put a second memory
+          // latency into every triangle test.
+          const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
           if (COUNT) np++;
           const uint32_t idbits = __float_as_uint(r0.w);
           const uint32_t type = idbits >> 30;
           const int id = (int)(idbits & 0x3fffffffu);
           float t = 0.f, be = 0.f, ga = 0.f;
-          bool hit;
-          if (type == PT_TRI) {
-            const float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-            hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
-          } else {
+          bool hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+          if (type != PT_TRI) {
             const Analytic* an = s.analytic + __float_as_int(r0.x);
             if (type == PT_SPHERE) {
               hit = sphereTest(__ldg(&an->a), o, d, tmin, tBest, !ANYHIT && id < bPrim, t);
+              be = ga = 0.f;
             } else {
               Analytic q;
               q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
@@ -160,10 +161,12 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           }
           if (hit) {
             if (ANYHIT) {
-              const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
-              if (__ldg(&m->kind) == MOX_MAT_DISNEY) {
-                if (__ldg((const int*)&m->dis.brdfType) == GLASS) atten *= mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
-                else { atten = mk3(0.f); tBits = 0u; gBits = 0u; sp = 0; }  // blocked: drop all pending work
+              // shadow class from the record itself (k_pack): only tinting glass still needs its material
+              const uint32_t cls = __float_as_uint(r1.w);
+              if (cls == MOX_SHADOW_BLOCKS) { atten = mk3(0.f); tBits = 0u; gBits = 0u; sp = 0; }  // blocked: drop all pending work
+              else if (cls == MOX_SHADOW_TINTS) {
+                const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
+                atten *= mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
               }
             } else {
               tBest = t; bPrim = id; bBeta = be; bGamma = ga;
