@@ -13,9 +13,6 @@
 #include "traverse.cuh"
 
 #define MOX_WIDE_STACK MOX_TRAVERSAL_STACK
-#ifndef MOX_VOTE_TRI_WEIGHT
-#define MOX_VOTE_TRI_WEIGHT 4  // a primitive step costs less than half a node step: vote by cost, not by head count (measured 1: 1115, 2: 1191, 3: 1206, 4: 1214, 6: 1207, 32: 1069 Mrays/s)
-#endif
 
 MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
 
@@ -26,8 +23,72 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   const unsigned ltMask = (1u << lane) - 1u;
   const uint32_t jobCount = job.countPtr ? __ldg(job.countPtr) : job.count;
   uint2 stack[MOX_WIDE_STACK];
-            stack[sp++] = make_uint2(gBase, gBits);
+  int sp = 0;
+  uint32_t gBase = 0, gBits = 0;  // node group
+  uint32_t tBase = 0, tBits = 0;  // primitive group
+  bool active = false, exhausted = false;
+  uint32_t rayId = 0, octinv = 0;
+  float3 o = mk3(0.f), d = mk3(0.f), idir = mk3(0.f);
+  float tmin = 0.f, tBest = 0.f, bBeta = 0.f, bGamma = 0.f;
+  int bPrim = -1;
+  float3 atten = mk3(1.f);
+  uint32_t nv = 0, np = 0;
+
+  while (true) {
+    // ---------------- refill idle lanes
+    if (!exhausted) {
+      unsigned idle = __ballot_sync(FULL, !active);
+      if (idle) {
+        const int leader = __ffs(idle) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(job.cursor, (uint32_t)__popc(idle));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          uint32_t i = base + __popc(idle & ltMask);
+          if (i < jobCount) {
+            rayId = job.queue ? MOX_LD_STREAM(job.queue + i) : i;
+            uint32_t oId = job.originMod ? rayId % job.originMod : rayId;
+            float4 ro = MOX_LD_STREAM(job.rayO + oId), rd = MOX_LD_STREAM(job.rayD + rayId);
+            if (!(ANYHIT && rd.w < 0.f)) {
+              RayPre r = prepRay(mk3(ro), mk3(rd), ro.w);
+              o = r.o; d = r.d; idir = r.idir; tmin = r.tmin;
+              octinv = 7u ^ ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
+              tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
+              atten = mk3(1.f);
+              sp = 0;
+              gBase = 0; gBits = 0x80000000u;  // root: one pending child, imask 0 -> node index 0
+              tBase = 0; tBits = 0;
+              active = true;
+              if (COUNT) { nv = 0; np = 0; }
+            }
           }
+        }
+        if (base + __popc(idle) >= jobCount) exhausted = true;
+      }
+    }
+    if (!__any_sync(FULL, active)) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---------------- traverse until too few lanes are busy
+    while (true) {
+      const bool isTri = active && tBits != 0u;
+      const bool isNode = active && !isTri && (gBits & 0xff000000u) != 0u;
+      const unsigned nm = __ballot_sync(FULL, isNode), tm = __ballot_sync(FULL, isTri);
+      const unsigned busy = nm | tm;
+      if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
+#ifndef MOX_VOTE_TRI_WEIGHT
+#define MOX_VOTE_TRI_WEIGHT 4  // a primitive step costs less than half a node step: vote by cost, not by head count (measured 1: 1115, 2: 1191, 3: 1206, 4: 1214, 6: 1207, 32: 1069 Mrays/s)
+#endif
+      if (__popc(nm) >= MOX_VOTE_TRI_WEIGHT * __popc(tm)) {
+        if (isNode) {
+          // ---- pop the front-most pending child of G
+          const uint32_t bit = 31u - (uint32_t)__clz(gBits & 0xff000000u);
+          const uint32_t imaskG = gBits & 0xffu;
+          gBits &= ~(1u << bit);
+          const uint32_t slot = (bit - 24u) ^ octinv;
+          const uint32_t nodeIdx = gBase + __popc(imaskG & ((1u << slot) - 1u));
+          if (gBits & 0xff000000u) stack[sp++] = make_uint2(gBase, gBits);
           // ---- fetch and test the node
           const BvhNode8* nd = s.nodes8 + nodeIdx;
           const float4 n0 = __ldg(&nd->n0), n1 = __ldg(&nd->n1), n2 = __ldg(&nd->n2), n3 = __ldg(&nd->n3), n4 = __ldg(&nd->n4);
