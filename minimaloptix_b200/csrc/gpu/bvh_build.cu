@@ -338,8 +338,8 @@ __global__ void k_emit2(int n, const uint32_t* __restrict__ sortedIds, const flo
 }
 
 __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const PrimDesc* __restrict__ prims,
-                       const TriIdx* __restrict__ tris, const float* __restrict__ verts, const GpuMaterial* __restrict__ mats,
-                       float4* __restrict__ packed) {
+                       const TriIdx* __restrict__ tris, const float* __restrict__ verts, const Analytic* __restrict__ analytic,
+                       const GpuMaterial* __restrict__ mats, float4* __restrict__ packed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t id = sortedIds[i];
@@ -351,7 +351,9 @@ __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const Prim
     const GpuMaterial* m = mats + (pd.typeMat >> 2);
     if (m->kind == MOX_MAT_DISNEY) shadowClass = m->dis.brdfType == GLASS ? MOX_SHADOW_TINTS : MOX_SHADOW_BLOCKS;
   }
-  const float sc = __uint_as_float(shadowClass);
+  // word 1 .w = shadow class, word 2 .w = the type tag again: the traversal derives the type from all three
+  // words, which keeps their loads together ahead of the type branch
+  const float sc = __uint_as_float(shadowClass), ty = __uint_as_float(type);
   float4* rec = packed + (size_t)i * MOX_PACKED_F4;
   if (type == PT_TRI) {
     TriIdx t = tris[pd.geom];
@@ -361,11 +363,16 @@ __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const Prim
     float3 e0 = p1 - p0, e1 = p0 - p2;
     rec[0] = make_float4(p0.x, p0.y, p0.z, __uint_as_float(idbits));
     rec[1] = make_float4(e0.x, e0.y, e0.z, sc);
-    rec[2] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    rec[2] = make_float4(e1.x, e1.y, e1.z, ty);
+  } else if (type == PT_SPHERE) {  // centre and radius inline: a sphere test needs no second fetch
+    const float4 cr = analytic[pd.geom].a;
+    rec[0] = make_float4(__int_as_float((int)pd.geom), 0.f, 0.f, __uint_as_float(idbits));
+    rec[1] = make_float4(cr.x, cr.y, cr.z, sc);
+    rec[2] = make_float4(cr.w, 0.f, 0.f, ty);
   } else {
     rec[0] = make_float4(__int_as_float((int)pd.geom), 0.f, 0.f, __uint_as_float(idbits));
     rec[1] = make_float4(0.f, 0.f, 0.f, sc);
-    rec[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[2] = make_float4(0.f, 0.f, 0.f, ty);
   }
 }
 
@@ -489,7 +496,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out.nInvalid = (int)hostSmall[6];
 
   if (nValid > 0 && (nValid <= 1 || !in.usePloc))
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.mats, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
   if (nValid <= 1) {
     BvhNode2 root;
     root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);
@@ -520,12 +527,12 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     std::string perr;
     if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
     if (out.maxDepth <= MOX_TRAVERSAL_STACK - 2) {
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, in.mats, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
     if (wantWide) {
       uint32_t* ordered8 = nullptr;
       const uint32_t rootId = (uint32_t)(nValid + nValid - 2);  // the last node PLOC created
       if (!wideCollapse(ploc, nValid, rootId, arena, out.nodes8, &ordered8, &out.nNodes8, &out.wideLevels, stream, perr)) return bail(perr);
-      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, in.mats, out.packed8);
+      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed8);
     }
     if (in.evStop) CKB(cudaEventRecord(in.evStop, stream));
     CKB(cudaStreamSynchronize(stream));
@@ -535,7 +542,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     return true;
     }
     // too deep for the traversal stack: fall through to the radix tree (depth <= 62)
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.mats, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
   }
   k_karras<<<divUp(nInner, B), B, 0, stream>>>(nValid, kin, children, range, parentInternal, parentLeaf);
   k_refit<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, boxLo, boxHi, children, parentInternal, parentLeaf, nodeLo, nodeHi, arrivals);

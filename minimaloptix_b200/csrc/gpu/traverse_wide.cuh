@@ -141,26 +141,25 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           const uint32_t k = 31u - (uint32_t)__clz(tBits);
           tBits &= ~(1u << k);
           const float4* rec = s.packed8 + (size_t)(tBase + k) * MOX_PACKED_F4;
-          // All three words are fetched and the triangle test runs before the type tag is looked at (for the
-          // rare analytic slot its result is discarded): waiting for the tag first would put a second memory
-          // latency into every triangle test.
+          // All three words are fetched before the type is known: the tag is folded from words 0 and 2 and the
+          // (zero) high bits of word 1, so the loads stay together ahead of the branch — waiting for word 0
+          // first would put a second memory latency into every triangle test.
           const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
           if (COUNT) np++;
           const uint32_t idbits = __float_as_uint(r0.w);
-          const uint32_t type = idbits >> 30;
+          const uint32_t type = (idbits >> 30) | __float_as_uint(r2.w) | (__float_as_uint(r1.w) >> 8);
           const int id = (int)(idbits & 0x3fffffffu);
           float t = 0.f, be = 0.f, ga = 0.f;
-          bool hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
-          if (type != PT_TRI) {
+          bool hit;
+          if (type == PT_TRI) {
+            hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+          } else if (type == PT_SPHERE) {
+            hit = sphereTest(make_float4(r1.x, r1.y, r1.z, r2.x), o, d, tmin, tBest, !ANYHIT && id < bPrim, t);
+          } else {
             const Analytic* an = s.analytic + __float_as_int(r0.x);
-            if (type == PT_SPHERE) {
-              hit = sphereTest(__ldg(&an->a), o, d, tmin, tBest, !ANYHIT && id < bPrim, t);
-              be = ga = 0.f;
-            } else {
-              Analytic q;
-              q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
-              hit = quadTest(q, o, d, tmin, t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
-            }
+            Analytic q;
+            q.a = __ldg(&an->a); q.b = __ldg(&an->b); q.c = __ldg(&an->c); q.d = __ldg(&an->d);
+            hit = quadTest(q, o, d, tmin, t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
           }
           if (hit) {
             if (ANYHIT) {

@@ -97,6 +97,11 @@ def soup_case(n_tris, out):
 
 def main():
     quick = "--quick" in sys.argv
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None   # e.g. --only C2
+    if only == "C2":
+        r = render_case("C2 random spheres 1920x1080 64spp thin lens", host.Scene.builtin("random_spheres"), 1920, 1080, 64, 5, 0x5EED, 0)
+        print(json.dumps({"mrays_per_s": r["gpu"]["mrays_per_s"], "stage_ms": r["gpu"]["stage_ms"]}))
+        return
     out = []
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     cornell = host.Scene.load(os.path.join(ROOT, "scenes", "cornell"), "cornell")
