@@ -291,7 +291,7 @@ def main():
                     "launches": launches, "avg_launch_ms": ms / max(launches, 1),
                     "share_of_step": ms / max(s1["ms_render"] - s0["ms_render"], 1e-9),
                     "note": "BVH + triangles are L2-resident (126 MB L2): the algorithmic bytes are served by L2, DRAM traffic is far "
-                            "smaller; ncu shows the kernel latency/issue-bound (profiles/r1_final_kernels_summary.txt)"}
+                            "smaller; ncu shows the kernel latency/issue-bound (profiles/r1_g_kernels_summary.txt)"}
 
         own_rays = rays_of(s1) - rays_of(s0)
         own_shadow = s1["rays_shadow_traced"] - s0["rays_shadow_traced"]
