@@ -75,12 +75,12 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
       const bool isTri = active && tBits != 0u;
       const bool isNode = active && !isTri && (gBits & 0xff000000u) != 0u;
       const unsigned nm = __ballot_sync(FULL, isNode), tm = __ballot_sync(FULL, isTri);
-      const unsigned busy = nm | tm;
-      if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
+      const int nNode = __popc(nm), nTri = __popc(tm);  // disjoint masks: busy lanes = nNode + nTri (POPC shares the slow conversion pipe)
+      if ((nm | tm) == 0u || (!exhausted && nNode + nTri < job.fetchThreshold)) break;
 #ifndef MOX_VOTE_TRI_WEIGHT
 #define MOX_VOTE_TRI_WEIGHT 4  // a primitive step costs less than half a node step: vote by cost, not by head count (measured 1: 1115, 2: 1191, 3: 1206, 4: 1214, 6: 1207, 32: 1069 Mrays/s)
 #endif
-      if (__popc(nm) >= MOX_VOTE_TRI_WEIGHT * __popc(tm)) {
+      if (nNode >= MOX_VOTE_TRI_WEIGHT * nTri) {
         if (isNode) {
           // ---- pop the front-most pending child of G
           const uint32_t bit = 31u - (uint32_t)__clz(gBits & 0xff000000u);
