@@ -18,7 +18,7 @@ namespace {
 constexpr int PL_THREADS = 256;
 constexpr int PL_ITEMS = 4;
 constexpr int PL_TILE = PL_THREADS * PL_ITEMS;
-constexpr int PL_MAX_RADIUS = 32;
+constexpr int PL_MAX_RADIUS = 128;
 
 __device__ __forceinline__ float mergedArea(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi) {
   float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
