@@ -173,7 +173,8 @@ def main():
     api = host.ApiTable(mox.GPU_LIB, "mox_")
     ctx = mox.gpu().context(local)
     sc.upload(api, ctx, W, H, MAX_DEPTH)
-    ctx.set_partition(rank, world, 32)
+    TILE = int(os.environ.get("MOX_BENCH_TILE", "32"))  # edge of the interleaved tiles (pixels)
+    ctx.set_partition(rank, world, TILE)
     build_ms = ctx.build_accel()
     cam = sc.cam_params(W, H)
 
@@ -222,6 +223,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    render_per_rank = [s1["ms_render"] - s0["ms_render"]]
+    if world > 1:
+        rr = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(rr, torch.tensor([render_per_rank[0]], dtype=torch.float64, device=dev))
+        render_per_rank = [round(x.item(), 2) for x in rr]
     dev_ms, wall_ms = t.tolist()
     rays_all, shadow_all, launches_all = cnt.tolist()
     value = rays_all / (dev_ms * 1e3)
@@ -261,7 +267,7 @@ def main():
     if rank == 0:
         cctx = mox.gpu().context(local)
         sc.upload(api, cctx, W, H, MAX_DEPTH)
-        cctx.set_partition(rank, world, 32)
+        cctx.set_partition(rank, world, TILE)
         cctx.build_accel(mox.structs.ACCEL_COUNTERS)
         cctx.render(1, SEED)
         cs = cctx.stats()
@@ -320,7 +326,7 @@ def main():
                 "spp_per_s": args.steps * SPP_PER_STEP / (dev_ms * 1e-3), "mshadow_per_s": shadow_all / (dev_ms * 1e3), "bvh_build_ms": build_ms,
                 "wall_ms_per_step": wall_ms / args.steps, "stage_ms": stage_ms,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 76 + 4, "d2h_bytes_per_step": int(d2h)},
-                "gather_bytes": tiles.bytes_on_the_wire(), "gather_ms": g0.elapsed_time(g1), "render_ms_rank0": s1["ms_render"] - s0["ms_render"], "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline_shadow if (roofline_shadow and roofline and roofline_shadow["share_of_step"] > roofline["share_of_step"]) else roofline,
+                "gather_bytes": tiles.bytes_on_the_wire(), "gather_ms": g0.elapsed_time(g1), "render_ms_rank0": s1["ms_render"] - s0["ms_render"], "render_ms_per_rank": render_per_rank, "tile": TILE, "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline_shadow if (roofline_shadow and roofline and roofline_shadow["share_of_step"] > roofline["share_of_step"]) else roofline,
                 "roofline_closest": roofline, "roofline_shadow": roofline_shadow, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:

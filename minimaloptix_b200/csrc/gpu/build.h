@@ -40,7 +40,9 @@ struct BuildInput {
   cudaEvent_t evStart = nullptr, evStop = nullptr;  // recorded around the build kernels when set
   DeviceArena* arena = nullptr;  // required
   bool usePloc = true;   // false: Karras radix tree (fastest build, lower quality)
-  int plocRadius = 32;  // measured on the bench scene: 8 -> 1152, 16 -> 1234, 32 -> 1247, 48 -> 1213, 64 -> 1219, 100 -> 1248 Mrays/s; build 3.5 -> 3.8 ms (16 -> 32)
+  int plocRadius = 0;    // 0 = automatic: 32 up to 2 M primitives, 16 above.  Bench scene (1 M): 8 -> 1152, 16 -> 1234, 32 -> 1247,
+                         // 48 -> 1213, 64 -> 1219, 100 -> 1248 Mrays/s, build 3.5 -> 3.8 ms (16 -> 32); 10 M soup: 16 -> 13.2 ms and
+                         // 652..856 Mrays/s, 32 -> 15.2 ms and 628..832
   bool useWide = true;   // collapse the PLOC tree into the compressed 8-wide BVH
 };
 

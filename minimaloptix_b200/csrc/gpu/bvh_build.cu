@@ -525,7 +525,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out.nNodes = nInner;
   if (in.usePloc) {
     std::string perr;
-    if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius, out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
+    if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius > 0 ? in.plocRadius : (nValid > 2000000 ? 16 : 32), out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
     if (out.maxDepth <= MOX_TRAVERSAL_STACK - 2) {
     k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
     if (wantWide) {

@@ -291,6 +291,36 @@ def test_wide_and_binary_traversal_render_identically(host, api_tables, gpu_back
     assert np.mean(imgs[0][0] == imgs[1][0]) > 0.999
 
 
+def test_shading_records_equal_the_gather_path(host, api_tables, gpu_backend, monkeypatch):
+    """The per-triangle 128-byte shading records hold exactly what the index gather reads (positions,
+    normals, uvs): images are bit-identical with `MOX_SHADE_RECORDS=0`, on a mesh scene with normals and on a
+    textured mesh with uvs."""
+    import tempfile
+    from test_host import _textured_scene
+
+    def render(sc, w, h, spp, cam=None):
+        out = []
+        for rec in ("1", "0"):
+            monkeypatch.setenv("MOX_SHADE_RECORDS", rec)   # read by mox_build_accel
+            g = gpu_backend.context(0)
+            sc.upload(api_tables.gpu, g, w, h, 5)
+            g.build_accel()
+            if cam is not None:
+                g.set_camera(cam)
+            g.render(spp, 21)
+            out.append((g.read_accum(), g.stats()["rays_bounce"], g.stats()["rays_shadow"]))
+        return out
+
+    a, b = render(host.Scene.builtin("interior", 30000), 160, 90, 3)
+    assert a[1:] == b[1:] and np.array_equal(a[0], b[0])
+    with tempfile.TemporaryDirectory() as tmp:
+        sc = host.Scene.load(_textured_scene(tmp), "tex")
+        cam = host.set_cam_params((0, 1.5, 2.5), (0, 0, 0), (0, 1, 0), 40, 1.0, 0.0, 1.0)
+        a, b = render(sc, 96, 96, 4, cam)
+        assert a[1:] == b[1:] and np.array_equal(a[0], b[0])
+        assert a[0].max() > 0
+
+
 def test_render_matches_oracle_philox(host, api_tables, orc, gpu_backend):
     sc = host.Scene.builtin("random_spheres")
     o, g = both(host, api_tables, orc, gpu_backend, sc, 160, 90, 5, 5)
