@@ -353,8 +353,8 @@ def test_jpeg_damaged_files_fail_cleanly(host):
             host.read_image(p)
 
 
-def _textured_scene(tmp):
-    """A unit quad mesh with uvs and a 4x4 checker texture, lit by one quad light."""
+def _textured_scene(tmp, tex_name="checker.png"):
+    """A unit quad mesh with uvs and a 4x4 checker texture (32x32 for JPEG: whole 8x8 blocks per cell), lit by one quad light."""
     from PIL import Image
     d = os.path.join(tmp, "tex")
     os.makedirs(d, exist_ok=True)
@@ -363,20 +363,24 @@ def _textured_scene(tmp):
     chk[1::2, 1::2] = [32, 255, 32]
     chk[::2, 1::2] = [32, 32, 255]
     chk[1::2, ::2] = [240, 240, 240]
-    Image.fromarray(chk).save(os.path.join(d, "checker.png"))
+    if tex_name.endswith(".jpg"):
+        Image.fromarray(np.kron(chk, np.ones((8, 8, 1), dtype=np.uint8))).save(os.path.join(d, tex_name), quality=95, subsampling="4:4:4")
+    else:
+        Image.fromarray(chk).save(os.path.join(d, tex_name))
     with open(os.path.join(d, "floor.obj"), "w") as f:
         f.write("v -1 0 -1\nv 1 0 -1\nv 1 0 1\nv -1 0 1\nvt 0 0\nvt 2 0\nvt 2 2\nvt 0 2\nvn 0 1 0\n"
                 "f 1/1/1 3/3/1 2/2/1\nf 1/1/1 4/4/1 3/3/1\n")
     with open(os.path.join(d, "tex.scene"), "w") as f:
-        f.write("material Checker\n{\n\tcolor 1 1 1\n\talbedoTex checker.png\n\troughness 0.6\n}\n"
+        f.write("material Checker\n{\n\tcolor 1 1 1\n\talbedoTex %s\n\troughness 0.6\n}\n"
                 "mesh\n{\n\tfile floor.obj\n\tmaterial Checker\n}\n"
-                "light\n{\n\ttype Quad\n\tposition -0.5 2 -0.5\n\tv1 0.5 2 -0.5\n\tv2 -0.5 2 0.5\n\temission 8 8 8\n}\n")
+                "light\n{\n\ttype Quad\n\tposition -0.5 2 -0.5\n\tv1 0.5 2 -0.5\n\tv2 -0.5 2 0.5\n\temission 8 8 8\n}\n" % tex_name)
     return d
 
 
-def test_textured_scene_loads_and_changes_the_oracle_image(host, orc):
+@pytest.mark.parametrize("tex_name", ["checker.png", "checker.jpg"])
+def test_textured_scene_loads_and_changes_the_oracle_image(host, orc, tex_name):
     with tempfile.TemporaryDirectory() as tmp:
-        d = _textured_scene(tmp)
+        d = _textured_scene(tmp, tex_name)
         sc = host.Scene.load(d, "tex")
         assert sc.texture_count() == 1 and sc.warnings() == []
         api = host.ApiTable(orc.ORACLE_LIB, "orc_")
