@@ -8,7 +8,8 @@
 // node step pops the front-most child of G (highest bit of slot ^ octant order), pushes the rest of
 // G, fetches the 80-byte node and tests its 8 quantised child boxes: one FMA per plane on a grid
 // local to the node, near/far planes picked per ray sign for four children at a time.  Warp phase
-// voting as in the binary kernel: a node step or one primitive test per iteration.
+// voting as in the binary kernel — a node step or one primitive test per iteration — but weighted by
+// cost (MOX_VOTE_TRI_WEIGHT): the cheaper primitive phase runs as soon as a quarter as many lanes want it.
 #pragma once
 #include "traverse.cuh"
 
