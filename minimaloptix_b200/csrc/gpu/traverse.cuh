@@ -52,6 +52,10 @@ MOX_D bool quadTest(const Analytic& q, const float3& o, const float3& d, float t
   return a2 >= 0 && a2 <= 1;
 }
 
+#ifndef MOX_VOTE_LEAF_WEIGHT
+#define MOX_VOTE_LEAF_WEIGHT 2  // weight of the primitive phase in the vote (binary BVH of the bench scene: 1 -> 1035, 2 -> 1057, 3 -> 1056 Mrays/s; the wide kernel uses 4)
+#endif
+
 struct RayPre { float3 o, d, idir; float tmin; };
 
 MOX_D RayPre prepRay(const float3& o, const float3& d, float tmin) {
@@ -164,7 +168,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
       const unsigned im = __ballot_sync(FULL, isInner), lm = __ballot_sync(FULL, isLeaf);
       const unsigned busy = im | lm;
       if (busy == 0u || (!exhausted && __popc(busy) < job.fetchThreshold)) break;
-      if (__popc(im) >= __popc(lm)) {
+      if (__popc(im) >= MOX_VOTE_LEAF_WEIGHT * __popc(lm)) {
         if (isInner) {  // one inner-node step
           const BvhNode2* nd = s.nodes + cur;
           float4 a = __ldg(&nd->c0xy), b = __ldg(&nd->c1xy), z = __ldg(&nd->cz);
