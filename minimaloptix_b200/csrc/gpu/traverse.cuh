@@ -94,10 +94,10 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
 // Persistent-thread traversal over the binary BVH with warp-level phase voting.
 //   * warps fetch rays from a global cursor: 32 at start, then whenever fewer than
 //     job.fetchThreshold lanes are still busy the idle lanes are refilled (Aila & Laine 2009);
-//   * every iteration the warp votes: if at least as many lanes sit at an inner node as at a leaf
-//     it runs ONE inner-node step (two child slabs, near child first), otherwise ONE primitive
-//     test for the lanes inside a leaf.  The branch is warp-uniform, so the executing phase always
-//     has at least half of the busy lanes active — a plain while-while loop measured 10 of 32;
+//   * every iteration the warp votes: if the lanes at an inner node outnumber MOX_VOTE_LEAF_WEIGHT x the
+//     lanes inside a leaf it runs ONE inner-node step (two child slabs, near child first), otherwise ONE
+//     primitive test for the lanes inside a leaf.  The branch is warp-uniform — a plain while-while loop
+//     measured 10 of 32 threads per instruction;
 //   * closest hit obeys the (t, id) lexicographic rule; any hit: Disney prims only, NORMAL
 //     blocks, GLASS tints (Material.cu:225-232);
 //   * per-lane traversal stack in local memory (far children only).
