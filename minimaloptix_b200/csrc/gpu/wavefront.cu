@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(TRAV_TPB, MOX_TRAV_MINBLOCKS) k_traverse(Scene
 }
 
 #ifndef MOX_WIDE_MINBLOCKS
-#define MOX_WIDE_MINBLOCKS 9   // 56 registers, no spills: measured 8 -> 1064, 9 -> 1090, 10 -> 1069 Mrays/s
+#define MOX_WIDE_MINBLOCKS 9   // 56 registers, no spills: measured 8 -> 1229, 9 -> 1258, 10 -> 1240 Mrays/s (before the weighted vote: 1064 / 1090 / 1069)
 #endif
 template <bool ANYHIT, bool COUNT>
 __global__ void __launch_bounds__(TRAV_TPB, MOX_WIDE_MINBLOCKS) k_traverse_wide(SceneView s, TraceJob job) {
