@@ -45,7 +45,10 @@ __device__ __forceinline__ uint32_t gridExponent(float extent) {
 // inner binary node: bit 0 = wide node, bits 1 + 3 (j - 2) .. = best k of C_distribute(n, j) for j = 2..8,
 // bit 22 + (i - 2) = "C(n, i) is C(n, i - 1)" for i = 2..7.  scripts/collapse_study.py is the numpy model of this
 // (4.5 - 5.4 % lower SAH cost than the greedy largest-area-first collapse on the bench scene).
-constexpr float kCostNode = 1.0f, kCostPrim = 0.43f;
+#ifndef MOX_COLLAPSE_PRIM_COST
+#define MOX_COLLAPSE_PRIM_COST 0.43f  // flat around it: 0.25 -> 1302, 0.43 -> 1307, 0.7 -> 1310 Mrays/s on the bench scene
+#endif
+constexpr float kCostNode = 1.0f, kCostPrim = MOX_COLLAPSE_PRIM_COST;
 
 __global__ void k_collapse_dp(int nLeaves, uint32_t root, const uint2* __restrict__ children, const uint32_t* __restrict__ parent,
                               const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi, const uint32_t* __restrict__ size,
