@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
-"""CPU study for the next round: how much SAH cost would an optimal collapse of the binary PLOC tree into the
-8-wide BVH save over the greedy largest-area-first collapse that bvh_wide.cu builds?
+"""CPU model of the wide collapse: how much SAH cost does the optimal collapse of the binary PLOC tree into the
+8-wide BVH (bvh_wide.cu::k_collapse_dp) save over the greedy largest-area-first collapse it replaced, and what
+would other leaf limits give?  (It predicted 4.5-5.4 % before the GPU version was written; the bench gained 4.2 %.)
 
 Emulates the GPU builder in numpy on the bench scene at a reduced triangle count (Morton order -> PLOC with the
 same radius -> binary tree), then collapses it twice:
   greedy   open the child with the largest surface area until there are 8 (subtrees of <= 2 primitives stay closed
-           as leaf children; free slots are then filled by opening those too) — what is built today;
+           as leaf children; free slots are then filled by opening those too) — MOX_WIDE_GREEDY=1, > 4 M primitives;
   optimal  the dynamic programme of Ylitie, Karras & Laine 2017 (C(n, i), i = 1..7, C_distribute(n, 8)).
 Cost model: c_node per visited wide node, c_prim per tested primitive, weighted by surface area (c_prim / c_node
 = 0.43: the measured instruction counts of a primitive step and a node step).  No GPU needed.
@@ -150,6 +151,10 @@ def main():
     print(f"{len(lo)} triangles, PLOC radius {radius}: binary nodes {len(L) - len(lo)}")
     print(f"greedy collapse : SAH cost {g:.3f}  ({n_wide} wide nodes, {fill:.2f} children per node)")
     print(f"optimal collapse: SAH cost {o:.3f}  ({100 * (1 - o / g):.1f} % lower)")
+    global LEAF_MAX
+    for lm in (1, 3, 4):   # what the programme would make of other leaf limits (the shipped limit is 2)
+        LEAF_MAX = lm
+        print(f"optimal collapse with leaf children of <= {lm} primitives: SAH cost {optimal_cost(L, R, A, size, root, len(lo)):.3f}")
 
 
 if __name__ == "__main__":
