@@ -10,7 +10,7 @@ same radius -> binary tree), then collapses it twice:
   optimal  the dynamic programme of Ylitie, Karras & Laine 2017 (C(n, i), i = 1..7, C_distribute(n, 8)).
 Cost model: c_node per visited wide node, c_prim per tested primitive, weighted by surface area (c_prim / c_node
 = 0.43: the measured instruction counts of a primitive step and a node step).  No GPU needed.
-usage: collapse_study.py [triangles=60000] [radius=32]"""
+usage: collapse_study.py [triangles=60000] [radius=32] [--topdown]"""
 import os
 import sys
 
@@ -75,6 +75,49 @@ def ploc(lo, hi, radius):
     return np.array(L), np.array(R), np.array(nlo), np.array(nhi), np.array(size)
 
 
+def topdown_sah(lo, hi, bins=16):
+    """Binned-SAH top-down binary tree (the classic CPU quality builder) over the same primitives: an estimate of
+    how much tree quality is left beyond PLOC.  Nodes are appended in post-order (children before parents)."""
+    sys.setrecursionlimit(100000)
+    n = len(lo)
+    L, R = [-1] * n, [-1] * n
+    nlo, nhi, size = [*lo], [*hi], [1] * n
+    cen = 0.5 * (lo + hi)
+
+    def build(ids):
+        if len(ids) == 1:
+            return int(ids[0])
+        blo, bhi = lo[ids].min(axis=0), hi[ids].max(axis=0)
+        best = (np.inf, None)
+        c = cen[ids]
+        cmin, cmax = c.min(axis=0), c.max(axis=0)
+        for ax in range(3):
+            if cmax[ax] <= cmin[ax]:
+                continue
+            b = np.minimum(((c[:, ax] - cmin[ax]) / (cmax[ax] - cmin[ax]) * bins).astype(int), bins - 1)
+            for split in range(1, bins):
+                left = b < split
+                nl = int(left.sum())
+                if nl == 0 or nl == len(ids):
+                    continue
+                il, ir = ids[left], ids[~left]
+                cost = area(lo[il].min(axis=0), hi[il].max(axis=0)) * nl + area(lo[ir].min(axis=0), hi[ir].max(axis=0)) * (len(ids) - nl)
+                if cost < best[0]:
+                    best = (cost, left)
+        if best[1] is None:
+            half = len(ids) // 2
+            il, ir = ids[:half], ids[half:]
+        else:
+            il, ir = ids[best[1]], ids[~best[1]]
+        a, b2 = build(il), build(ir)
+        L.append(a); R.append(b2)
+        nlo.append(blo); nhi.append(bhi); size.append(len(ids))
+        return len(L) - 1
+
+    build(np.arange(n))
+    return np.array(L), np.array(R), np.array(nlo), np.array(nhi), np.array(size)
+
+
 def greedy_cost(L, R, A, size, root):
     total_nodes = total_leaf = 0.0
     count = 0
@@ -130,8 +173,9 @@ def optimal_cost(L, R, A, size, root, n_prims):
 
 
 def main():
-    n_tris = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
-    radius = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n_tris = int(args[0]) if len(args) > 0 else 60000
+    radius = int(args[1]) if len(args) > 1 else 32
     sc = host.Scene.builtin("interior", n_tris)
     tris = []
     for m in range(sc.info().n_meshes):
@@ -151,6 +195,12 @@ def main():
     print(f"{len(lo)} triangles, PLOC radius {radius}: binary nodes {len(L) - len(lo)}")
     print(f"greedy collapse : SAH cost {g:.3f}  ({n_wide} wide nodes, {fill:.2f} children per node)")
     print(f"optimal collapse: SAH cost {o:.3f}  ({100 * (1 - o / g):.1f} % lower)")
+    if "--topdown" in sys.argv:
+        L2, R2, nlo2, nhi2, size2 = topdown_sah(lo, hi)
+        root2 = len(L2) - 1
+        A2 = area(nlo2, nhi2) / area(nlo2[root2], nhi2[root2])
+        o2 = optimal_cost(L2, R2, A2, size2, root2, len(lo))
+        print(f"binned-SAH top-down tree, optimal collapse: SAH cost {o2:.3f}  ({100 * (1 - o2 / o):.1f} % below PLOC + optimal collapse)")
     global LEAF_MAX
     for lm in (1, 3, 4):   # what the programme would make of other leaf limits (the shipped limit is 2)
         LEAF_MAX = lm
