@@ -27,7 +27,7 @@ all: oracle host gpu
 gpu: $(PKG)/libmox.so
 host: $(PKG)/libmox_host.so $(PKG)/mox_cli
 oracle: oracle/liboracle.so
-ref: oracle/_ref/libref_loader.so
+ref: oracle/_ref/libref_loader.so oracle/_ref/libref_render.so
 
 $(PKG)/libmox.so: $(GPU_SRCS) $(GPU_HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(GPU_SRCS) -lcudart
@@ -46,6 +46,15 @@ oracle/_ref/libref_loader.so: oracle/ref_shim/ref_loader.cpp oracle/ref_shim/opt
 	@if [ -d $(REF) ]; then mkdir -p oracle/_ref/inc && ln -sf $(REF)/Structures.h oracle/_ref/inc/structures.h && \
 	  $(CXX) -O1 -std=c++14 -fPIC -w -shared -Ioracle/ref_shim -Ioracle/_ref/inc -I$(REF) -o $@ \
 	     oracle/ref_shim/ref_loader.cpp $(REF)/scene.cpp ; \
+	else echo "reference not present: skipping oracle/_ref"; fi
+
+# Reference render half: Camera.cu, Geometry.cu, Material.cu, miss.cu, Exception.cu, disney.h and
+# utils_device.h compiled unchanged from /root/reference behind the OptiX shim in
+# oracle/ref_shim/render/ (every product and sum rounded separately, like the oracle).
+oracle/_ref/libref_render.so: oracle/ref_shim/ref_render.cpp oracle/ref_shim/render/optix_world.h include/mox.h
+	@if [ -d $(REF) ]; then mkdir -p oracle/_ref/inc && ln -sf $(REF)/Structures.h oracle/_ref/inc/structures.h && \
+	  $(CXX) -O2 -std=c++14 -fPIC -shared -pthread -ffp-contract=off -fno-fast-math -Wno-narrowing -Wno-sign-compare \
+	     -Ioracle/ref_shim/render -Ioracle/_ref/inc -I$(REF) -o $@ oracle/ref_shim/ref_render.cpp ; \
 	else echo "reference not present: skipping oracle/_ref"; fi
 
 clean:

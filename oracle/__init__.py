@@ -16,6 +16,7 @@ _vp, _u32, _i32p, _f3 = C.c_void_p, C.c_uint32, C.POINTER(C.c_int32), C.c_float 
 _EXTRA = {
     "set_threads": (C.c_int, [_vp, C.c_int]),
     "set_brute_force": (C.c_int, [_vp, C.c_int]),
+    "set_quad_light_draw_order": (C.c_int, [_vp, C.c_int]),
     "tea16": (_u32, [_u32, _u32]),
     "lcg": (_u32, [_i32p]),
     "rand": (C.c_float, [_i32p]),

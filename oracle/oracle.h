@@ -47,6 +47,10 @@ int orc_trace_shadow(orc_ctx*, const float* rays, size_t n, float* out_rgb);
 /* oracle-only knobs */
 int orc_set_threads(orc_ctx*, int n_threads);       /* 0 = hardware_concurrency */
 int orc_set_brute_force(orc_ctx*, int on);          /* 1 = test every primitive (id ground truth) */
+/* Which of the two draws of `light.u * rand(s) + light.v * rand(s)` (Material.cu:180) scales u:
+ * 0 = the first (pinned convention, nvcc's order), 1 = the second (g++'s order; used only when
+ * comparing against the reference compiled with g++ in oracle/_ref). */
+int orc_set_quad_light_draw_order(orc_ctx*, int order);
 /* unit-test hooks for the restated device functions */
 uint32_t orc_tea16(uint32_t v0, uint32_t v1);
 uint32_t orc_lcg(int32_t* seed);
@@ -61,6 +65,21 @@ void orc_refine_hitpoint(const float hit[3], const float dir[3], const float n[3
                          float back[3], float front[3]);
 int orc_refract(const float i[3], const float n[3], float ior, float out[3]);
 float orc_fresnel(float cosI, float cosT, float ior);
+void orc_rand_in_unit_sphere(int32_t* seed, float out[3]);
+void orc_rand_in_unit_disk(int32_t* seed, float out[3]);
+int32_t orc_fork_seed(int32_t parentSeed, int32_t parentDepth);
+void orc_offset(const float hit[3], const float n[3], float out[3]);
+float orc_gtr1(float NdotH, float a);
+float orc_gtr2(float NdotH, float a);
+float orc_gtr2_aniso(float NdotH, float HdotX, float HdotY, float ax, float ay);
+float orc_schlick_fresnel(float u);
+float orc_smith_ggx(float NdotV, float alphaG);
+float orc_smith_ggx_aniso(float NdotV, float VdotX, float VdotY, float ax, float ay);
+float orc_power_heuristic(float a, float b);
+void orc_srgb2lin(const float v[3], float out[3]);
+/* closest hit + the five intersection attributes (n x 15 floats); bbox-program bounds */
+int orc_trace_closest_attrs(orc_ctx*, const float* rays, size_t n, void* hits, float* attrs);
+int orc_prim_bounds(orc_ctx*, uint32_t prim, float out[6], int* valid);
 #ifdef __cplusplus
 }
 #endif
