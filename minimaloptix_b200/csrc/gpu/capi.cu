@@ -647,6 +647,9 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   if (!c) return MOX_ERR_INVALID;
   int rc = bind(c);
   if (rc) return rc;
+  // A failed rebuild must not leave a context that still claims to be built.
+  c->built = false;
+  c->wideBuilt = false;
   cudaStreamSynchronize(c->stream);
   if ((rc = upload(c, c->dPrims, c->prims))) return rc;
   if ((rc = upload(c, c->dTris, c->tris))) return rc;

@@ -151,49 +151,3 @@ struct DisneyHit {
   }
 };
 
-MOX_D float disneyPdf(const DisneyParams& mp, const float3& N, const float3& L, const float3& H) {
-  float diffuseRatio = 0.5f * (1.0f - mp.metallic);
-  float specularAlpha = fmaxf(0.001f, mp.roughness);
-  float clearcoatAlpha = lerpf(0.1f, 0.001f, mp.clearcoatGloss);
-  float specularRatio = 1.f - diffuseRatio;
-  float cosTheta = fabsf(dot(N, H));
-  float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha) * cosTheta;
-  float pdfGTR2 = GTR2(cosTheta, specularAlpha) * cosTheta;
-  float ratio = 1.0f / (1.0f + mp.clearcoat);
-  float pdfH = lerpf(pdfGTR1, pdfGTR2, ratio);
-  float pdfL = pdfH / (4.0f * fabsf(dot(L, H)));
-  float pdfDiff = fabsf(dot(N, L)) / MOX_PI_F;
-  return diffuseRatio * pdfDiff + specularRatio * pdfL;
-}
-
-MOX_D float3 disneyEval(const DisneyParams& mp, const float3& baseColor, const float3& N, const float3& L,
-                        const float3& V, const float3& H) {
-  Onb3 onb(N);
-  float NdotL = dot(N, L), NdotV = dot(N, V), NdotH = dot(N, H), LdotH = dot(L, H);
-  float3 Cdlin = mk3(powf(baseColor.x, 2.2f), powf(baseColor.y, 2.2f), powf(baseColor.z, 2.2f));
-  float Cdlum = dot(Cdlin, mk3(0.3f, 0.6f, 0.1f));
-  float3 Ctint = Cdlum > 0.f ? Cdlin / Cdlum : mk3(1.f);
-  float3 Cspec0 = lerp3(mp.specular * 0.08f * lerp3(mk3(1.f), Ctint, mp.specularTint), Cdlin, mp.metallic);
-  float3 Csheen = lerp3(mk3(1.f), Ctint, mp.sheenTint);
-  float FL = schlickFresnel(NdotL), FV = schlickFresnel(NdotV);
-  float Fd90 = 0.5f + 2.f * LdotH * LdotH * mp.roughness;
-  float Fd = lerpf(1.f, Fd90, FL) * lerpf(1.f, Fd90, FV);
-  float Fss90 = LdotH * LdotH * mp.roughness;
-  float Fss = lerpf(1.0f, Fss90, FL) * lerpf(1.0f, Fss90, FV);
-  float ss = 1.25f * (Fss * (1.f / (NdotL + NdotV) - 0.5f) + 0.5f);
-  float aspect = sqrtf(1 - mp.anisotropic * 0.9f);
-  float ax = fmaxf(.001f, sqr(mp.roughness) / aspect);
-  float ay = fmaxf(.001f, sqr(mp.roughness) * aspect);
-  float3 X = normalize(onb.tangent);
-  float3 Y = normalize(cross(N, X));
-  float Ds = GTR2Aniso(NdotH, dot(H, X), dot(H, Y), ax, ay);
-  float FH = schlickFresnel(LdotH);
-  float3 Fs = lerp3(Cspec0, mk3(1.f), FH);
-  float Gs = smithGGgxAniso(NdotL, dot(L, X), dot(L, Y), ax, ay) * smithGGgxAniso(NdotV, dot(V, X), dot(V, Y), ax, ay);
-  float3 Fsheen = FH * mp.sheen * Csheen;
-  float Dr = GTR1(NdotH, lerpf(0.1f, 0.001f, mp.clearcoatGloss));
-  float Fr = lerpf(0.04f, 1.f, FH);
-  float Gr = smithGGgx(NdotL, 0.25f) * smithGGgx(NdotV, 0.25f);
-  return ((1.0f / MOX_PI_F) * lerpf(Fd, ss, mp.subsurface) * Cdlin + Fsheen) * (1.0f - mp.metallic) + Gs * Fs * Ds +
-         mk3(0.25f * mp.clearcoat * Gr * Fr * Dr);
-}

@@ -232,8 +232,15 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
       }
       if (active && cur == MOX_DONE) {  // ray finished
         if (ANYHIT) {
-          float4 c = job.shC[rayId];
-          job.shC[rayId] = make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w);
+          // same three cases as the wide kernel, so both report bit-identical results even when the
+          // precomputed contribution is not finite: blocked -> 0 (the reference skips the term,
+          // Material.cu:192), unoccluded -> untouched, tinted -> multiply
+          if (atten.x == 0.f && atten.y == 0.f && atten.z == 0.f) {
+            job.shC[rayId] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (atten.x != 1.f || atten.y != 1.f || atten.z != 1.f) {
+            float4 c = job.shC[rayId];
+            job.shC[rayId] = make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w);
+          }
         } else {
           MOX_ST_STREAM(job.hits + rayId, make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma));
         }

@@ -412,7 +412,14 @@ __global__ void __launch_bounds__(TPB) k_accumulate(LaunchCtx c, uint32_t nSampl
   uint32_t bad = 0;
   for (uint32_t s = 0; s < nSamples; ++s) {
     float4 r = c.pb.rad[(size_t)s * c.nOwned + j];
-    if (!isfinite(r.x) || !isfinite(r.y) || !isfinite(r.z)) bad++;
+    if (!isfinite(r.x) || !isfinite(r.y) || !isfinite(r.z)) {
+      // The reference paints badColor when a launch index raises an OptiX exception (Exception.cu:10-12,
+      // MinimalOptiX.cpp:149-151).  A NaN/Inf sample is this path's exception: badColor instead of the
+      // sample, counted in mox_stats.nonfinite_samples.
+      bad++;
+      acc.x += c.rp.bad.x; acc.y += c.rp.bad.y; acc.z += c.rp.bad.z;
+      continue;
+    }
     acc.x += clampf(r.x, 0.f, 1.f);
     acc.y += clampf(r.y, 0.f, 1.f);
     acc.z += clampf(r.z, 0.f, 1.f);

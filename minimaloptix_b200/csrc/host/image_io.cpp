@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 namespace moxh {
@@ -348,14 +349,20 @@ bool readImageRgba(const std::string& path, int& w, int& h, std::vector<float>& 
   }
   if (f.size() > 2 && f[0] == 'P' && (f[1] == '6' || f[1] == '5' || f[1] == 'F' || f[1] == 'f')) {
     // netpbm header: magic, width, height, maxval (or scale for PFM), one whitespace, data
+    // The header is text of unknown length inside a binary buffer: parse a NUL-terminated copy
+    // of its first bytes so strtod can never run past the end of a truncated file.
+    const std::string head((const char*)f.data(), std::min<size_t>(f.size(), 512));
     size_t pos = 2;
     double vals[3];
     for (int k = 0; k < 3; ++k) {
-      while (pos < f.size() && (isspace(f[pos]) || f[pos] == '#')) { if (f[pos] == '#') while (pos < f.size() && f[pos] != '\n') ++pos; else ++pos; }
+      while (pos < head.size() && (isspace((unsigned char)head[pos]) || head[pos] == '#')) { if (head[pos] == '#') while (pos < head.size() && head[pos] != '\n') ++pos; else ++pos; }
+      if (pos >= head.size()) { err = "truncated netpbm header"; return false; }
       char* end = nullptr;
-      vals[k] = strtod((const char*)&f[pos], &end);
-      pos = (size_t)(end - (const char*)f.data());
+      vals[k] = strtod(head.c_str() + pos, &end);
+      if (end == head.c_str() + pos) { err = "bad netpbm header"; return false; }
+      pos = (size_t)(end - head.c_str());
     }
+    if (pos >= f.size()) { err = "truncated netpbm header"; return false; }
     ++pos;
     w = (int)vals[0]; h = (int)vals[1];
     if (w <= 0 || h <= 0) { err = "bad netpbm header"; return false; }

@@ -31,7 +31,14 @@ void SceneDesc::addQuad(const float3& anchor, const float3& v1, const float3& v2
   setQuadParams(anchor, v1, v2, it.quad);
   items.push_back(it);
 }
-int SceneDesc::addMesh(MeshDesc&& mesh, const MaterialBlock& m) {
+bool SceneDesc::addMesh(MeshDesc&& mesh, const MaterialBlock& m, std::string& err) {
+  const int nv = (int)(mesh.v.size() / 3), nn = (int)(mesh.n.size() / 3), nt = (int)(mesh.uv.size() / 2);
+  for (size_t f = 0; f < mesh.vi.size(); ++f) {
+    if (mesh.vi[f] < 0 || mesh.vi[f] >= nv) { err = "face " + std::to_string(f / 3) + " names vertex " + std::to_string(mesh.vi[f]) + " of " + std::to_string(nv); return false; }
+    // -1 = "no normal / texcoord" (tinyobj); anything else must exist
+    if (f < mesh.ni.size() && mesh.ni[f] != -1 && (mesh.ni[f] < 0 || mesh.ni[f] >= nn)) { err = "face " + std::to_string(f / 3) + " names normal " + std::to_string(mesh.ni[f]) + " of " + std::to_string(nn); return false; }
+    if (f < mesh.ti.size() && mesh.ti[f] != -1 && (mesh.ti[f] < 0 || mesh.ti[f] >= nt)) { err = "face " + std::to_string(f / 3) + " names texcoord " + std::to_string(mesh.ti[f]) + " of " + std::to_string(nt); return false; }
+  }
   for (size_t f = 0; f < mesh.vi.size(); ++f) {
     int i = mesh.vi[f];
     aabb.include(mk3(mesh.v[3 * i], mesh.v[3 * i + 1], mesh.v[3 * i + 2]));
@@ -42,7 +49,7 @@ int SceneDesc::addMesh(MeshDesc&& mesh, const MaterialBlock& m) {
   Item it; it.type = Item::MESH_ITEM; it.mesh = (int)meshes.size() - 1; it.mat = m;
   memset(&it.sphere, 0, sizeof it.sphere); memset(&it.quad, 0, sizeof it.quad);
   items.push_back(it);
-  return it.mesh;
+  return true;
 }
 CamParams SceneDesc::camParams(uint32_t width, uint32_t height) const {
   CamParams c;
@@ -211,7 +218,13 @@ bool loadSceneFile(SceneDesc& s, const std::string& sceneDir, const std::string&
         m.ni[f] = sh.mesh.indices[f].normal_index;
         m.ti[f] = sh.mesh.indices[f].texcoord_index;
       }
-      s.addMesh(std::move(m), disney(scene.materials[i]));
+      // The OBJ reader keeps tinyobj's index arithmetic (any positive or relative index is
+      // accepted), so a malformed file can name a vertex that does not exist: refuse the file,
+      // as mox_add_mesh would at upload.
+      if (!s.addMesh(std::move(m), disney(scene.materials[i]), err)) {
+        err = scene.meshNames[i] + ": " + err;
+        return false;
+      }
       s.items.back().texture = texIndex;
     }
   }
@@ -225,7 +238,10 @@ bool loadSceneFile(SceneDesc& s, const std::string& sceneDir, const std::string&
     }
   }
   s.lights = scene.lights;
-  if (scene.width > 0 && scene.height > 0) { /* parsed but unused by the reference renderer */ }
+  // properties{ width W  height H } (scene.cpp:93-101): the reference parses them and then renders at
+  // its compiled-in 1920x1080; here they are the scene's default image size, which the
+  // CLI uses when --width/--height are not given.
+  if (scene.width > 0 && scene.height > 0) { s.defaultWidth = (uint32_t)scene.width; s.defaultHeight = (uint32_t)scene.height; }
 
   const CamRule* rule = nullptr;
   for (auto& r : kCamRules) if (name == r.name) rule = &r;

@@ -63,7 +63,9 @@ struct SceneDesc {
 
   void addSphere(const SphereParams& s, const MaterialBlock& m);
   void addQuad(const float3& anchor, const float3& v1, const float3& v2, const MaterialBlock& m);
-  int addMesh(MeshDesc&& mesh, const MaterialBlock& m);  // returns mesh index
+  // Validates every index against the attribute arrays first; false + err on a bad one.
+  bool addMesh(MeshDesc&& mesh, const MaterialBlock& m, std::string& err);
+  void addMesh(MeshDesc&& mesh, const MaterialBlock& m) { std::string e; addMesh(std::move(mesh), m, e); }  // generated meshes
   CamParams camParams(uint32_t width, uint32_t height) const;
 };
 

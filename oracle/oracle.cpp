@@ -491,7 +491,9 @@ float3 cameraSample(const orc_ctx& c, uint32_t x, uint32_t y, int32_t launchSeed
   ray.tmin = c.eps;
   ray.tmax = RT_DEFAULT_MAX;
   float3 color = trace(c, ray, 1, rng, cnt);
-  if (!std::isfinite(color.x) || !std::isfinite(color.y) || !std::isfinite(color.z)) cnt.nonfinite++;
+  // A non-finite sample is this path's "exception": badColor replaces it (Exception.cu:10-12; the
+  // reference's clamp would turn NaN into 1 per channel — SURVEY App. A.8, a stated deviation).
+  if (!std::isfinite(color.x) || !std::isfinite(color.y) || !std::isfinite(color.z)) { cnt.nonfinite++; return c.bad; }
   return clamp(color, make_float3(0.f), make_float3(1.f));
 }
 

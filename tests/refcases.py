@@ -242,7 +242,7 @@ def _disney(**kw):
     return d
 
 
-def build_zoo(ctx, host, w, h, depth=5):
+def build_zoo(ctx, host, w, h, depth=5, textured=True):
     """Every program in one scene: Disney NORMAL with all lobes switched on (textured mesh with
     normals + uvs, a metallic anisotropic tessellated sphere, a clearcoat / sheen / subsurface /
     emissive analytic sphere), one Disney GLASS sphere, lambertian / metal / glass analytic
@@ -264,7 +264,8 @@ def build_zoo(ctx, host, w, h, depth=5):
     fn /= np.linalg.norm(fn, axis=1, keepdims=True)
     fuv = np.array([[0, 0], [2.5, 0], [2.5, 2.5], [0, 2.5]], np.float32)
     fi = np.array([[0, 2, 1], [0, 3, 2]], np.int32)
-    ctx.add_mesh(fv, fi, S.MAT_DISNEY, _disney(albedoID=tid, roughness=0.6, sheen=0.3), normals=fn, n_idx=fi, texcoords=fuv, t_idx=fi)
+    floor = _disney(albedoID=tid, roughness=0.6, sheen=0.3) if textured else _disney(color=(0.6, 0.55, 0.5), roughness=0.6, sheen=0.3)
+    ctx.add_mesh(fv, fi, S.MAT_DISNEY, floor, normals=fn, n_idx=fi, texcoords=fuv, t_idx=fi)
     v, n, uv, f = _uv_sphere((-1.6, 0.8, 0.2), 0.8)
     ctx.add_mesh(v, f, S.MAT_DISNEY, _disney(color=(0.9, 0.6, 0.2), metallic=0.8, roughness=0.3, anisotropic=0.6, specularTint=0.4),
                  normals=n, n_idx=f, texcoords=uv, t_idx=f)

@@ -239,8 +239,9 @@ def image_metrics(a, b, n):
     return rmse, within, rel
 
 
-# (scene kind, loader, w, h, spp, depth): rng=ref, equal seeds: RMSE <= 2e-3 and >= 99.9 % of
-# pixels within 1/255 after quantisation (SURVEY.md §8d tolerance ii).
+# (scene kind, loader, w, h, spp, depth): rng=ref, equal seeds.  SURVEY.md §8d tolerance (ii) allows RMSE <= 2e-3;
+# measured values are 4e-10 ... 1.3e-6 with equal ray counts, so the assertions hold the suite to RMSE <= 1e-5 and
+# to equal counts up to the few Disney paths whose branch decision flips on a 1-ulp libm difference.
 RENDER_CASES = [
     ("spheres_lens", None, 160, 90, 8, 5, 0xC0FFEE),
     ("spheres_pinhole", None, 160, 90, 8, 5, 0xC0FFEE),
@@ -269,11 +270,13 @@ def test_render_matches_oracle_ref_rng(host, api_tables, orc, gpu_backend, case)
           "oracle", so["rays_primary"], so["rays_bounce"], so["rays_shadow"])
     assert sg["nonfinite_samples"] == so["nonfinite_samples"] == 0
     assert sg["rays_primary"] == so["rays_primary"] == w * h * spp
-    assert abs(sg["rays_bounce"] - so["rays_bounce"]) <= 1e-3 * so["rays_bounce"]
-    assert abs(sg["rays_shadow"] - so["rays_shadow"]) <= 1e-3 * max(so["rays_shadow"], 1)
-    assert rmse <= 2e-3
-    assert within >= 0.999
-    assert rel <= 5e-3
+    assert abs(sg["rays_bounce"] - so["rays_bounce"]) <= 1e-5 * so["rays_bounce"] + 1
+    assert abs(sg["rays_shadow"] - so["rays_shadow"]) <= 1e-5 * so["rays_shadow"] + 1
+    if so["rays_shadow"] == 0:
+        assert sg["rays_bounce"] == so["rays_bounce"]   # no Disney shading: IEEE-exact operations only
+    assert rmse <= 1e-5
+    assert within >= 0.9999
+    assert rel <= 1e-5
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "scenes", "coffee", "coffee.scene")), reason="scenes/coffee not fetched")
@@ -313,6 +316,130 @@ def test_textured_disney_matches_oracle(host, api_tables, orc, gpu_backend):
         img = a / 8
         assert (img[..., 0] > 2 * img[..., 1] + 0.02).any() and (img[..., 1] > 2 * img[..., 0] + 0.02).any()
         assert rmse <= 2e-3 and within >= 0.995 and rel <= 5e-3
+
+
+# BASELINE configs 1-3 at THEIR resolution (spp reduced where the config's spp would take the oracle minutes):
+# (name, width, height, spp, seed, Disney?)  Non-Disney scenes use only IEEE-exact operations (+ - * / sqrt), so
+# every branch decision is the oracle's and the ray counts must be EQUAL; Disney shading calls sinf/cosf/powf/logf,
+# where CUDA and glibc differ by an ulp, so a handful of `N.L > 0` / `pdf > 0` decisions per million paths may flip.
+FULL_SIZE_CASES = [
+    ("cornell", 512, 512, 16, 0xC0FFEE, True),          # config 1 exactly: 512x512, 16 spp, depth 5
+    ("random_spheres", 1920, 1080, 2, 0x5EED, False),   # config 2 at 1920x1080, thin lens
+    ("coffee", 1920, 1080, 1, 0xC0FFEE, True),          # config 3 at 1080p
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE_CASES, ids=[c[0] for c in FULL_SIZE_CASES])
+def test_baseline_configs_at_full_resolution(host, api_tables, orc, gpu_backend, case):
+    name, w, h, spp, seed, is_disney = case
+    if name == "random_spheres":
+        sc = host.Scene.builtin(name)
+    else:
+        d = os.path.join(ROOT, "scenes", name)
+        if not os.path.exists(os.path.join(d, name + ".scene")):
+            pytest.skip(f"scenes/{name} not present")
+        sc = host.Scene.load(d, name)
+    o, g = both(host, api_tables, orc, gpu_backend, sc, w, h, 5)
+    o.render(spp, seed)
+    g.render(spp, seed)
+    so, sg = o.stats(), g.stats()
+    rmse, within, rel = image_metrics(g.read_accum(), o.read_accum(), spp)
+    print(name, f"{w}x{h}x{spp}", "rmse", rmse, "within1", within, "rel", rel, "bounce", sg["rays_bounce"], so["rays_bounce"],
+          "shadow", sg["rays_shadow"], so["rays_shadow"])
+    assert sg["nonfinite_samples"] == so["nonfinite_samples"] == 0
+    assert sg["rays_primary"] == so["rays_primary"] == w * h * spp
+    if not is_disney:
+        assert sg["rays_bounce"] == so["rays_bounce"]
+        assert rmse <= 1e-5 and within == 1.0
+    elif name == "cornell":
+        assert abs(sg["rays_bounce"] - so["rays_bounce"]) <= 4e-6 * so["rays_bounce"]
+        assert abs(sg["rays_shadow"] - so["rays_shadow"]) <= 4e-6 * so["rays_shadow"]
+        assert rmse <= 1e-5 and within >= 0.99999
+    else:
+        # coffee: roughness 0.001-0.01 makes GTR2 so peaked that 1-ulp differences in sinf/cosf/powf move
+        # individual highlight samples (stated tolerance of SURVEY §8d ii)
+        assert abs(sg["rays_bounce"] - so["rays_bounce"]) <= 1e-3 * so["rays_bounce"]
+        assert abs(sg["rays_shadow"] - so["rays_shadow"]) <= 1e-3 * so["rays_shadow"]
+        assert rmse <= 1e-3 and within >= 0.999 and rel <= 5e-3
+
+
+@pytest.mark.parametrize("mode", [S.RNG_REF, S.RNG_PHILOX], ids=["ref", "philox"])
+@pytest.mark.parametrize("textured", [False, True], ids=["plain", "textured"])
+def test_zoo_every_program_matches_oracle(host, orc, gpu_backend, mode, textured):
+    """The scene of tests/refcases.py that runs every program — Disney NORMAL with all lobes, Disney GLASS, a
+    SPHERE light (volume sampling, Material.cu:177-179; corrected sphere box, Geometry.cu:57-63) next to a QUAD
+    light, lambertian / metal / glass — on the GPU against the oracle, in both RNG modes (Philox x Disney)."""
+    import refcases as R
+    o, g = orc.context(), gpu_backend.context(0)
+    for ctx in (o, g):
+        R.build_zoo(ctx, host, 240, 160, 5, textured=textured)
+        ctx.set_rng_mode(mode)
+        ctx.render(8, 0xD15EA5E)
+    so, sg = o.stats(), g.stats()
+    rmse, within, rel = image_metrics(g.read_accum(), o.read_accum(), 8)
+    print("zoo", mode, textured, "rmse", rmse, "within1", within, "rel", rel, sg["rays_bounce"], so["rays_bounce"], sg["rays_shadow"], so["rays_shadow"])
+    assert sg["nonfinite_samples"] == so["nonfinite_samples"] == 0
+    assert sg["rays_primary"] == so["rays_primary"]
+    assert sg["rays_shadow"] > sg["rays_primary"]            # two lights, most hits are Disney
+    assert abs(sg["rays_bounce"] - so["rays_bounce"]) <= 1e-5 * so["rays_bounce"] + 2
+    assert abs(sg["rays_shadow"] - so["rays_shadow"]) <= 1e-5 * so["rays_shadow"] + 2
+    if textured:   # hardware bilinear filter (9-bit weights) vs float filter in the oracle
+        assert rmse <= 2e-3 and within >= 0.995
+    else:
+        assert rmse <= 1e-5 and within >= 0.9999
+    # primitive ids, t, beta, gamma against brute force on incoherent rays through the zoo
+    ob = orc.context(brute_force=True)
+    R.build_zoo(ob, host, 16, 16, 5, textured=textured)
+    nbad, nhit = check_ids(ob, g, random_rays(100000, [-4, 0.01, -4], [4, 4, 4], 12), "zoo")
+    assert nhit > 50000 and nbad <= 2
+    # shadow transmittance incl. the tinting GLASS sphere
+    rays = random_rays(50000, [-4, 0.01, -4], [4, 4, 4], 13, tmax=3.0)
+    assert np.any(ob.trace_shadow(rays) != g.trace_shadow(rays), axis=1).sum() <= 2
+
+
+def test_nonfinite_samples_become_bad_color(host, orc, gpu_backend):
+    """Exception.cu:10-12 / MinimalOptiX.cpp:149-151: badColor is what the reference paints when a launch index
+    fails.  Here a NaN/Inf sample is that failure: a Disney material with a negative colour makes pow(c, 2.2) NaN.
+    Custom badColor; oracle and GPU agree, count the same samples, and a pixel fully covered by the bad sphere is
+    exactly spp x badColor."""
+    bad = (0.25, 0.5, 0.75)
+    d = S.DisneyParams()
+    d.color = S.float3(-1.0, 0.5, 0.5); d.specular = d.roughness = d.sheenTint = 0.5; d.clearcoatGloss = 1.0
+    lq = S.LightParams()
+    lq.position, lq.u, lq.v, lq.normal = S.float3(-1, 3, -1), S.float3(2, 0, 0), S.float3(0, 0, 2), S.float3(0, -1, 0)
+    lq.area, lq.emission, lq.shape = 4.0, S.float3(5, 5, 5), S.QUAD
+    imgs, stats = [], []
+    for ctx in (orc.context(), gpu_backend.context(0)):
+        ctx.set_globals(64, 64, 5, bad=bad, bg=(0.1, 0.1, 0.1))
+        ctx.set_camera(host.set_cam_params((0, 0, 4), (0, 0, 0), (0, 1, 0), 30, 1.0, 0.0, 1.0))
+        ctx.add_sphere(S.SphereParams(0.7, S.float3(0, 0, 0), S.float3()), S.MAT_DISNEY, d)
+        ctx.add_quad(host.set_quad_params((-1, 3, -1), (2, 0, 0), (0, 0, 2)), S.MAT_LIGHT, lq)
+        ctx.set_lights([lq])
+        ctx.build_accel()
+        ctx.render(4, 3)
+        imgs.append(ctx.read_accum()); stats.append(ctx.stats())
+    assert stats[0]["nonfinite_samples"] == stats[1]["nonfinite_samples"] > 1000
+    assert np.allclose(imgs[0], imgs[1], atol=1e-5)
+    assert np.array_equal(imgs[1][32, 32], 4 * np.array(bad, np.float32))      # centre pixel: every sample hits the sphere
+    assert np.allclose(imgs[1][1, 1], 4 * 0.1)                                # corner: background only
+
+
+def test_sorted_ray_queue_is_bit_identical(host, api_tables, gpu_backend, monkeypatch):
+    """MOX_SORT_RAYS=1 reorders the extend queue (3-pass radix sort by origin cell + direction octant inside the
+    bounce loop): every per-path result is order-independent, so image and ray counts are bit-identical."""
+    sc = host.Scene.builtin("interior", 30000)
+    out = []
+    for sort in ("0", "1"):
+        monkeypatch.setenv("MOX_SORT_RAYS", sort)    # read by mox_create
+        g = gpu_backend.context(0)
+        sc.upload(api_tables.gpu, g, 200, 120, 5)
+        g.build_accel()
+        g.render(3, 31)
+        st = g.stats()
+        out.append((g.read_accum(), st["rays_bounce"], st["rays_shadow"], st["kernel_launches"]))
+    assert out[0][1:3] == out[1][1:3]
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert out[1][3] > out[0][3]    # the sort kernels did run
 
 
 def test_wide_and_binary_traversal_render_identically(host, api_tables, gpu_backend):
@@ -371,7 +498,8 @@ def test_render_matches_oracle_philox(host, api_tables, orc, gpu_backend):
         ctx.set_rng_mode(S.RNG_PHILOX)
         ctx.render(4, 99)
     rmse, within, rel = image_metrics(g.read_accum(), o.read_accum(), 4)
-    assert rmse <= 2e-3 and within >= 0.999
+    assert o.stats()["rays_bounce"] == g.stats()["rays_bounce"]
+    assert rmse <= 1e-5 and within >= 0.9999
 
 
 def test_batched_render_equals_single_launches(host, api_tables, gpu_backend):
