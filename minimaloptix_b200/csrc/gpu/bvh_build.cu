@@ -349,9 +349,16 @@ __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const Prim
   uint32_t shadowClass = MOX_SHADOW_INVISIBLE;
   if (mats) {
     const GpuMaterial* m = mats + (pd.typeMat >> 2);
-    if (m->kind == MOX_MAT_DISNEY) shadowClass = m->dis.brdfType == GLASS ? MOX_SHADOW_TINTS : MOX_SHADOW_BLOCKS;
+    uint32_t cls = MOX_CLASS_LAMBERT;
+    if (m->kind == MOX_MAT_DISNEY) {
+      shadowClass = m->dis.brdfType == GLASS ? MOX_SHADOW_TINTS : MOX_SHADOW_BLOCKS;
+      cls = m->dis.brdfType == GLASS ? MOX_CLASS_DIELECTRIC : MOX_CLASS_DISNEY;
+    } else if (m->kind == MOX_MAT_METAL) cls = MOX_CLASS_METAL;
+    else if (m->kind == MOX_MAT_GLASS) cls = MOX_CLASS_DIELECTRIC;
+    else if (m->kind == MOX_MAT_LIGHT) cls = MOX_CLASS_LIGHT;
+    shadowClass |= cls << MOX_CLASS_SHIFT;   // stays below 256: the traversal folds (word >> 8) into the type tag
   }
-  // word 1 .w = shadow class, word 2 .w = the type tag again: the traversal derives the type from all three
+  // word 1 .w = shadow class | shade class << 2, word 2 .w = the type tag again: the traversal derives the type from all three
   // words, which keeps their loads together ahead of the type branch
   const float sc = __uint_as_float(shadowClass), ty = __uint_as_float(type);
   float4* rec = packed + (size_t)i * MOX_PACKED_F4;
@@ -411,7 +418,8 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);  // empty children: a point box no ray reaches
     root.ref = make_int4(MOX_EMPTY_CHILD, MOX_EMPTY_CHILD, 0, 0);
     if (!ensureOut(1, 1)) { err = "out of device memory"; return false; }
-    CK(cudaMemcpy(out.nodes, &root, sizeof root, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(out.nodes, &root, sizeof root, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
     out.nNodes = 1;
     if (in.evStart) CK(cudaEventRecord(in.evStart, stream));
     if (in.evStop) CK(cudaEventRecord(in.evStop, stream));

@@ -51,7 +51,7 @@ struct DevBuf {
 struct mox_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr;
   std::string err;
 
   RenderParams rp{};
@@ -99,7 +99,24 @@ struct mox_ctx {
   std::vector<DevBuf> otherOwned;  // cached owned lists of other ranks (unpack)
   std::vector<uint64_t> ownedCount; // cached |owned pixels| per rank of the current partition
 
-  PathBuffers pb;
+  // The owned pixels of a batch are rendered as `nSlices` independent sub-batches ("slices"), each with its own
+  // path buffers and stream: while the host reads one slice's material counts back, and while that slice's
+  // persistent traversal kernel drains its last rays, the other slice's kernels keep the SMs busy.
+  struct Slice {
+    PathBuffers pb;
+    cudaStream_t stream = nullptr;   // slice 0 uses the context stream
+    cudaEvent_t evReady = nullptr;   // the counters of the bounce in flight have landed in hostCnt
+    uint32_t* hostCnt = nullptr;     // pinned: C_WORDS + BOUNCE_RING * C_BOUNCE_WORDS
+    StageTimer timer;
+    // state of the batch in flight
+    LaunchCtx lc;
+    uint32_t S = 0, bound = 0, depth = 0, matCount[Q_COUNT] = {0, 0, 0, 0};
+    int iCur = 0, iNext = 1, iSpare = 2;
+    bool done = true;
+  };
+  static constexpr int kMaxSlices = 4;
+  Slice slices[kMaxSlices];
+  int nSlices = 2;
   float* pinned = nullptr;
   size_t pinnedBytes = 0;
 
@@ -109,7 +126,6 @@ struct mox_ctx {
   double msRender = 0, msBuild = 0;
   double msStage[ST_COUNT] = {0, 0, 0, 0, 0};
   uint64_t extendLaunches = 0, kernelLaunches = 0;
-  StageTimer timer;
   size_t maxBatchPaths = 32u << 20;  // paths per wavefront (~280 B each with 4 lights); measured 4 Mi -> 947, 32 Mi -> 980 Mrays/s at 4K
   bool sortRays = false;         // reorder the extend queue by (origin cell, direction octant) from bounce 2 on
   float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {1, 1, 1};
@@ -184,7 +200,9 @@ int refreshOwned(mox_ctx* c) {
   if (c->dOwned) cudaFree(c->dOwned);
   c->dOwned = nullptr;
   CUCK(c, cudaMalloc(&c->dOwned, std::max<size_t>(l.size(), 1) * 4));
-  if (!l.empty()) CUCK(c, cudaMemcpy(c->dOwned, l.data(), l.size() * 4, cudaMemcpyHostToDevice));
+  // Stream-ordered upload: a plain cudaMemcpy from pageable memory may return before the DMA has landed, and
+  // the context stream is non-blocking, so a kernel launched next could still read stale bytes.
+  if (!l.empty()) { CUCK(c, cudaMemcpyAsync(c->dOwned, l.data(), l.size() * 4, cudaMemcpyHostToDevice, c->stream)); CUCK(c, cudaStreamSynchronize(c->stream)); }
   c->nOwned = (uint32_t)l.size();
   for (auto& b : c->otherOwned) b.release();
   c->otherOwned.clear();
@@ -203,32 +221,44 @@ void freePaths(PathBuffers& pb) {
   pb = PathBuffers();
 }
 
-int ensurePaths(mox_ctx* c, size_t paths, size_t nLights, size_t nSeeds) {
-  PathBuffers& pb = c->pb;
+constexpr size_t kCounterWords = C_WORDS + BOUNCE_RING * C_BOUNCE_WORDS;
+
+// Bytes of wavefront state per path (see PathBuffers): rays, hit, throughput, radiance, RNG state, three queue
+// buffers, two key buffers, four material queues; per light a direction, a contribution and a queue entry; one
+// shadow origin when there are lights.
+size_t bytesPerPath(size_t nLights) { return 16 * 4 + 8 + 4 + 3 * 4 + 2 * 4 + 4 * 4 + (nLights ? 16 + nLights * 36 : 0); }
+
+int ensurePaths(mox_ctx* c, PathBuffers& pb, cudaStream_t stream, size_t paths, size_t nLights, size_t nSeeds) {
   size_t slots = paths * nLights;
   if (pb.capacity < paths || pb.shadowSlots < slots || !pb.counters) {
-    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(stream);
+    // grow geometrically so that a slowly growing sample count does not reallocate on every call
+    if (pb.capacity && paths > pb.capacity) paths = std::max(paths, pb.capacity + pb.capacity / 2);
+    slots = paths * nLights;
     size_t seedCap = pb.seedCap;
     int32_t* seeds = pb.seeds;
     pb.seeds = nullptr;
     freePaths(pb);
     pb.seeds = seeds; pb.seedCap = seedCap;
     CUCK(c, cudaMalloc(&pb.rayO, paths * 16)); CUCK(c, cudaMalloc(&pb.rayD, paths * 16));
-    CUCK(c, cudaMalloc(&pb.hit, paths * 16)); CUCK(c, cudaMalloc(&pb.thr, paths * 16));
+    CUCK(c, cudaMalloc(&pb.hit, paths * 8)); CUCK(c, cudaMalloc(&pb.thr, paths * 16));
     CUCK(c, cudaMalloc(&pb.rad, paths * 16)); CUCK(c, cudaMalloc(&pb.state, paths * 4));
     for (auto& q : pb.qBuf) CUCK(c, cudaMalloc(&q, paths * 4));
-    for (auto& k : pb.kBuf) CUCK(c, cudaMalloc(&k, paths * 4));
-    CUCK(c, cudaMalloc(&pb.sortScratch, radixSortScratchBytes(paths)));
+    if (c->sortRays) {
+      for (auto& k : pb.kBuf) CUCK(c, cudaMalloc(&k, paths * 4));
+      CUCK(c, cudaMalloc(&pb.sortScratch, radixSortScratchBytes(paths)));
+    }
     for (auto& q : pb.qMat) CUCK(c, cudaMalloc(&q, paths * 4));
     if (slots) {
       CUCK(c, cudaMalloc(&pb.shO, paths * 16)); CUCK(c, cudaMalloc(&pb.shD, slots * 16)); CUCK(c, cudaMalloc(&pb.shC, slots * 16));
       CUCK(c, cudaMalloc(&pb.shQueue, slots * 4));
     }
-    CUCK(c, cudaMalloc(&pb.counters, C_WORDS * 4));
-    CUCK(c, cudaMemset(pb.counters, 0, C_WORDS * 4));
+    CUCK(c, cudaMalloc(&pb.counters, kCounterWords * 4));
+    CUCK(c, cudaMemset(pb.counters, 0, kCounterWords * 4));
     pb.capacity = paths; pb.shadowSlots = slots;
   }
   if (pb.seedCap < nSeeds) {
+    cudaStreamSynchronize(stream);
     cudaFree(pb.seeds);
     pb.seeds = nullptr;
     CUCK(c, cudaMalloc(&pb.seeds, nSeeds * 4));
@@ -304,105 +334,206 @@ int syncLights(mox_ctx* c) {
   return MOX_OK;
 }
 
-// One wavefront batch: `seeds.size()` samples of every owned pixel.
+inline uint32_t* bounceBlock(const PathBuffers& pb, uint32_t depth) { return pb.counters + C_WORDS + (depth % BOUNCE_RING) * C_BOUNCE_WORDS; }
+
+int ensureSlice(mox_ctx* c, int k) {
+  mox_ctx::Slice& sl = c->slices[k];
+  if (!sl.stream) {
+    if (k == 0) sl.stream = c->stream;
+    else CUCK(c, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  }
+  if (!sl.evReady) CUCK(c, cudaEventCreateWithFlags(&sl.evReady, cudaEventDisableTiming));
+  if (!sl.hostCnt) CUCK(c, cudaMallocHost(&sl.hostCnt, kCounterWords * 4));
+  return MOX_OK;
+}
+
+// Enqueue one bounce of a slice up to the point where the host needs numbers: extend (persistent traversal, ray
+// count read on the device), classify, and the read-back of the counters.
+int sliceEnqueueExtend(mox_ctx* c, mox_ctx::Slice& sl) {
+  LaunchCtx& lc = sl.lc;
+  StageTimer& tm = sl.timer;
+  const uint32_t depth = sl.depth;
+  lc.bc = bounceBlock(sl.pb, depth);
+  // bounce 1 traces exactly `bound` camera rays; later bounces read the number of spawned rays from the previous
+  // bounce's counter block, `bound` (what was shaded) only sizes the grids
+  const uint32_t* countPtr = depth == 1 ? nullptr : bounceBlock(sl.pb, depth - 1) + C_NEXT;
+  tm.begin(ST_EXTEND, sl.stream);
+  launchExtend(lc, lc.pb.qCur, sl.bound, countPtr, depth);
+  tm.end(sl.stream);
+  tm.begin(ST_SHADE, sl.stream);
+  launchClassify(lc, lc.pb.qCur, sl.bound, countPtr, depth);
+  tm.end(sl.stream);
+  c->extendLaunches++; c->kernelLaunches += 2;
+  CUCK(c, cudaMemcpyAsync(sl.hostCnt, sl.pb.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, sl.stream));
+  CUCK(c, cudaEventRecord(sl.evReady, sl.stream));
+  return MOX_OK;
+}
+
+int sliceFinish(mox_ctx* c, mox_ctx::Slice& sl) {
+  StageTimer& tm = sl.timer;
+  tm.begin(ST_ACCUMULATE, sl.stream);
+  launchAccumulate(sl.lc, sl.S);
+  tm.end(sl.stream);
+  c->kernelLaunches++;
+  CUCK(c, cudaMemcpyAsync(sl.hostCnt, sl.pb.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, sl.stream));
+  CUCK(c, cudaEventRecord(sl.evReady, sl.stream));
+  sl.done = true;
+  return MOX_OK;
+}
+
+// The counters of the bounce in flight have arrived: shade what was binned, trace the shadow rays, and enqueue
+// the next bounce — or the accumulation when nothing is left.
+int sliceAdvance(mox_ctx* c, mox_ctx::Slice& sl) {
+  LaunchCtx& lc = sl.lc;
+  StageTimer& tm = sl.timer;
+  PathBuffers& pb = sl.pb;
+  const uint32_t depth = sl.depth;
+  const uint32_t* hostBounce = sl.hostCnt + C_WORDS + (depth % BOUNCE_RING) * C_BOUNCE_WORDS;
+  if (depth == 1) c->raysPrimary += sl.bound;
+  else {  // exact number of rays this bounce traced, and of shadow rays the previous one queued
+    const uint32_t* prev = sl.hostCnt + C_WORDS + ((depth - 1) % BOUNCE_RING) * C_BOUNCE_WORDS;
+    c->raysBounce += prev[C_NEXT];
+    c->raysShadowTraced += prev[C_SHQ];
+  }
+  uint32_t any = 0;
+  for (int k = 0; k < Q_COUNT; ++k) { sl.matCount[k] = hostBounce[C_MAT0 + k]; any += sl.matCount[k]; }
+  if (!any) return sliceFinish(c, sl);
+  tm.begin(ST_SHADE, sl.stream);
+  for (int k = 0; k < Q_COUNT; ++k) { launchShade(lc, k, sl.matCount[k], depth); if (sl.matCount[k]) c->kernelLaunches++; }
+  tm.end(sl.stream);
+  if (sl.matCount[Q_DISNEY] && lc.scene.nLights) {
+    tm.begin(ST_SHADOW, sl.stream);
+    launchShadow(lc, sl.matCount[Q_DISNEY]);
+    tm.end(sl.stream);
+    tm.begin(ST_SHADE, sl.stream);
+    launchApply(lc, sl.matCount[Q_DISNEY]);
+    tm.end(sl.stream);
+    c->kernelLaunches += 2;
+  }
+  // the block bounce depth+1 will use was last written BOUNCE_RING bounces ago
+  CUCK(c, cudaMemsetAsync(bounceBlock(pb, depth + 1), 0, C_BOUNCE_WORDS * 4, sl.stream));
+  uint32_t bound = any;   // every shaded path spawns at most one ray
+  if (c->sortRays) {
+    // reordering needs the exact count on the host: one more round trip (this mode is an experiment, off by default)
+    CUCK(c, cudaMemcpyAsync(sl.hostCnt, pb.counters, kCounterWords * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CUCK(c, cudaStreamSynchronize(sl.stream));
+    bound = hostBounce[C_NEXT];
+  }
+  if (c->sortRays && bound > 4096) {
+    // 24-bit keys -> 3 passes: the sorted queue lands in (kBuf[1], qBuf[iSpare])
+    tm.begin(ST_SHADE, sl.stream);
+    radixSortAsync(pb.kBuf[0], pb.qBuf[sl.iNext], pb.kBuf[1], pb.qBuf[sl.iSpare], (int)bound, 3, pb.sortScratch, sl.stream);
+    tm.end(sl.stream);
+    c->kernelLaunches += 5;
+    int t = sl.iCur; sl.iCur = sl.iSpare; sl.iSpare = sl.iNext; sl.iNext = t;
+  } else {
+    int t = sl.iCur; sl.iCur = sl.iNext; sl.iNext = t;
+  }
+  lc.pb.qCur = pb.qBuf[sl.iCur]; lc.pb.qNext = pb.qBuf[sl.iNext];
+  sl.bound = bound;
+  sl.depth = depth + 1;
+  if (!bound) return sliceFinish(c, sl);
+  return sliceEnqueueExtend(c, sl);
+}
+
+// One wavefront batch: `seeds.size()` samples of every owned pixel, rendered as nSlices interleaved sub-batches.
 int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
   const uint32_t S = (uint32_t)seeds.size();
   const size_t P = (size_t)S * c->nOwned;
   if (P == 0) return MOX_OK;
   if (P > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "batch too large");
-  // Size the wavefront buffers for a full batch right away (not for this call's sample count), so
-  // a later call with more samples per pixel does not reallocate inside its timed region.
-  const size_t fullBatch = std::max<size_t>(1, c->maxBatchPaths / c->nOwned) * (size_t)c->nOwned;
-  int rc = ensurePaths(c, std::max(P, fullBatch), c->lights.size(), std::max<size_t>(S, fullBatch / c->nOwned));
-  if (rc) return rc;
-  PathBuffers& pb = c->pb;
-  CUCK(c, cudaMemcpyAsync(pb.seeds, seeds.data(), S * 4, cudaMemcpyHostToDevice, c->stream));
-  LaunchCtx lc;
-  lc.scene = sceneView(c);
-  lc.rp = c->rp;
-  lc.pb = pb;
-  lc.ownedPix = c->dOwned;
-  lc.nOwned = c->nOwned;
-  lc.accu = c->dAccu;
-  lc.countTraversal = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
-  lc.stream = c->stream;
-  lc.sceneLo = make_float3(c->sceneLo[0], c->sceneLo[1], c->sceneLo[2]);
-  {
-    float ex = c->sceneHi[0] - c->sceneLo[0], ey = c->sceneHi[1] - c->sceneLo[1], ez = c->sceneHi[2] - c->sceneLo[2];
-    lc.sceneInvExt = make_float3(ex > 0 ? 128.f / ex : 0.f, ey > 0 ? 128.f / ey : 0.f, ez > 0 ? 128.f / ez : 0.f);
+  int K = c->nSlices;
+  if (P < (size_t)K * 65536 || c->nOwned < (uint32_t)K) K = 1;   // tiny batches: the second stream buys nothing
+  int rc;
+  // slice k renders the owned pixels [first_k, first_k+1) — all S samples of a pixel stay in one slice, in launch
+  // order, so the accumulated sums do not depend on the number of slices
+  uint32_t first[mox_ctx::kMaxSlices + 1];
+  for (int k = 0; k <= K; ++k) first[k] = (uint32_t)((uint64_t)c->nOwned * k / K);
+  // all allocations first: a failure (MOX_ERR_OOM -> the caller retries with a smaller batch) must not leave
+  // work of another slice in flight
+  for (int k = 0; k < K; ++k) {
+    if ((rc = ensureSlice(c, k))) return rc;
+    if ((rc = ensurePaths(c, c->slices[k].pb, c->slices[k].stream, (size_t)S * (first[k + 1] - first[k]), c->lights.size(), S))) return rc;
   }
-  int iCur = 0, iNext = 1, iSpare = 2;
-  lc.pb.qCur = pb.qBuf[iCur]; lc.pb.qNext = pb.qBuf[iNext];
-  lc.pb.qKey = c->sortRays ? pb.kBuf[0] : nullptr;
-
-  CUCK(c, cudaMemsetAsync(pb.counters, 0, C_WORDS * 4, c->stream));
-  StageTimer& tm = c->timer;
-  tm.begin(ST_GENERATE, c->stream);
-  launchGenerate(lc, S);
-  tm.end(c->stream);
-  c->kernelLaunches++;
-  uint32_t count = (uint32_t)P;
-  uint32_t host[C_WORDS];
-  for (uint32_t depth = 1; count > 0; ++depth) {
-    if (depth == 1) c->raysPrimary += count; else c->raysBounce += count;
-    tm.begin(ST_EXTEND, c->stream);
-    launchExtend(lc, lc.pb.qCur, count, depth);
-    tm.end(c->stream);
-    tm.begin(ST_SHADE, c->stream);
-    launchLogic(lc, lc.pb.qCur, count, depth);
-    tm.end(c->stream);
-    c->extendLaunches++; c->kernelLaunches += 2;
-    CUCK(c, cudaMemcpyAsync(host, pb.counters, 8 * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUCK(c, cudaStreamSynchronize(c->stream));
-    uint32_t matCount[Q_COUNT];
-    uint32_t any = 0;
-    for (int k = 0; k < Q_COUNT; ++k) { matCount[k] = host[C_MAT0 + k]; any += matCount[k]; }
-    if (!any) break;
-    tm.begin(ST_SHADE, c->stream);
-    for (int k = 0; k < Q_COUNT; ++k) { launchShade(lc, k, matCount[k], depth); if (matCount[k]) c->kernelLaunches++; }
-    tm.end(c->stream);
-    if (matCount[Q_DISNEY] && lc.scene.nLights) {
-      tm.begin(ST_SHADOW, c->stream);
-      launchShadow(lc, matCount[Q_DISNEY]);
-      tm.end(c->stream);
-      tm.begin(ST_SHADE, c->stream);
-      launchApply(lc, matCount[Q_DISNEY]);
-      tm.end(c->stream);
-      c->kernelLaunches += 2;
+  cudaEvent_t evStart = c->evFork;
+  CUCK(c, cudaEventRecord(evStart, c->stream));
+  for (int k = 0; k < K; ++k) {
+    mox_ctx::Slice& sl = c->slices[k];
+    const uint32_t nPix = first[k + 1] - first[k];
+    const size_t paths = (size_t)S * nPix;
+    if (k) CUCK(c, cudaStreamWaitEvent(sl.stream, evStart, 0));   // scene uploads happened on the context stream
+    PathBuffers& pb = sl.pb;
+    CUCK(c, cudaMemcpyAsync(pb.seeds, seeds.data(), S * 4, cudaMemcpyHostToDevice, sl.stream));
+    LaunchCtx& lc = sl.lc;
+    lc.scene = sceneView(c);
+    lc.rp = c->rp;
+    lc.pb = pb;
+    lc.ownedPix = c->dOwned + first[k];
+    lc.nOwned = nPix;
+    lc.accu = c->dAccu;
+    lc.countTraversal = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
+    lc.stream = sl.stream;
+    lc.sceneLo = make_float3(c->sceneLo[0], c->sceneLo[1], c->sceneLo[2]);
+    {
+      float ex = c->sceneHi[0] - c->sceneLo[0], ey = c->sceneHi[1] - c->sceneLo[1], ez = c->sceneHi[2] - c->sceneLo[2];
+      lc.sceneInvExt = make_float3(ex > 0 ? 128.f / ex : 0.f, ey > 0 ? 128.f / ey : 0.f, ez > 0 ? 128.f / ez : 0.f);
     }
-    CUCK(c, cudaMemcpyAsync(host, pb.counters, 8 * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUCK(c, cudaMemsetAsync(pb.counters, 0, 8 * 4, c->stream));  // next count + material counts + shadow queue length
-    CUCK(c, cudaStreamSynchronize(c->stream));
-    count = host[C_NEXT];
-    c->raysShadowTraced += host[C_SHQ];
-    if (c->sortRays && count > 4096) {
-      // 24-bit keys -> 3 passes: the sorted queue lands in (kBuf[1], qBuf[iSpare])
-      tm.begin(ST_SHADE, c->stream);
-      radixSortAsync(pb.kBuf[0], pb.qBuf[iNext], pb.kBuf[1], pb.qBuf[iSpare], (int)count, 3, pb.sortScratch, c->stream);
-      tm.end(c->stream);
-      c->kernelLaunches += 5;
-      int t = iCur; iCur = iSpare; iSpare = iNext; iNext = t;
-    } else {
-      int t = iCur; iCur = iNext; iNext = t;
-    }
-    lc.pb.qCur = pb.qBuf[iCur]; lc.pb.qNext = pb.qBuf[iNext];
+    sl.iCur = 0; sl.iNext = 1; sl.iSpare = 2;
+    lc.pb.qCur = pb.qBuf[sl.iCur]; lc.pb.qNext = pb.qBuf[sl.iNext];
+    lc.pb.qKey = c->sortRays ? pb.kBuf[0] : nullptr;
+    lc.bc = bounceBlock(pb, 1);
+    sl.S = S; sl.bound = (uint32_t)paths; sl.depth = 1; sl.done = false;
+    CUCK(c, cudaMemsetAsync(pb.counters, 0, kCounterWords * 4, sl.stream));
+    sl.timer.begin(ST_GENERATE, sl.stream);
+    launchGenerate(lc, S);
+    sl.timer.end(sl.stream);
+    c->kernelLaunches++;
+    if (!paths) { sl.done = true; CUCK(c, cudaEventRecord(sl.evReady, sl.stream)); continue; }
+    if ((rc = sliceEnqueueExtend(c, sl))) return rc;
   }
-  tm.begin(ST_ACCUMULATE, c->stream);
-  launchAccumulate(lc, S);
-  tm.end(c->stream);
-  c->kernelLaunches++;
-  CUCK(c, cudaMemcpyAsync(host, pb.counters, C_WORDS * 4, cudaMemcpyDeviceToHost, c->stream));
-  CUCK(c, cudaStreamSynchronize(c->stream));
+  // Round-robin over the slices: wait for one slice's counters, enqueue its next stage, move on.  While the host
+  // sits in cudaEventSynchronize for slice A, slice B's kernels are already queued on the GPU.
+  for (int live = K; live > 0;) {
+    live = 0;
+    for (int k = 0; k < K; ++k) {
+      mox_ctx::Slice& sl = c->slices[k];
+      if (sl.done) continue;
+      CUCK(c, cudaEventSynchronize(sl.evReady));
+      if ((rc = sliceAdvance(c, sl))) return rc;
+      if (!sl.done) live++;
+    }
+  }
+  // join: every slice's accumulation and final counter read-back
+  for (int k = 0; k < K; ++k) {
+    mox_ctx::Slice& sl = c->slices[k];
+    CUCK(c, cudaEventSynchronize(sl.evReady));
+    if (k) CUCK(c, cudaStreamWaitEvent(c->stream, sl.evReady, 0));
+    const uint32_t* host = sl.hostCnt;
+    sl.timer.collect(c->msStage);
+    c->nonfinite += host[C_NONFINITE];
+    c->raysShadow += host[C_SHADOW];
+    c->nodeVisits += ((uint64_t)host[C_NODEVIS_HI] << 32) | host[C_NODEVIS_LO];
+    c->primTests += ((uint64_t)host[C_PRIMTEST_HI] << 32) | host[C_PRIMTEST_LO];
+    c->nodeVisitsShadow += ((uint64_t)host[C_NODEVIS_SH_LO + 1] << 32) | host[C_NODEVIS_SH_LO];
+    c->primTestsShadow += ((uint64_t)host[C_PRIMTEST_SH_LO + 1] << 32) | host[C_PRIMTEST_SH_LO];
+  }
   CUCK(c, cudaGetLastError());
-  tm.collect(c->msStage);
-  c->nonfinite += host[C_NONFINITE];
-  c->raysShadow += host[C_SHADOW];
-  c->nodeVisits += ((uint64_t)host[C_NODEVIS_HI] << 32) | host[C_NODEVIS_LO];
-  c->primTests += ((uint64_t)host[C_PRIMTEST_HI] << 32) | host[C_PRIMTEST_LO];
-  c->nodeVisitsShadow += ((uint64_t)host[C_NODEVIS_SH_LO + 1] << 32) | host[C_NODEVIS_SH_LO];
-  c->primTestsShadow += ((uint64_t)host[C_PRIMTEST_SH_LO + 1] << 32) | host[C_PRIMTEST_SH_LO];
   c->launches += S;
   return MOX_OK;
+}
+
+// Paths per batch: the configured cap, lowered so that the wavefront state fits into 60 % of the free device
+// memory for this scene's light count (36 bytes per path and light).
+size_t batchCap(mox_ctx* c) {
+  size_t cap = c->maxBatchPaths;
+  size_t freeB = 0, totalB = 0;
+  if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+    size_t have = 0;
+    for (auto& sl : c->slices) have += sl.pb.capacity * bytesPerPath(sl.pb.capacity ? sl.pb.shadowSlots / sl.pb.capacity : 0);
+    size_t budget = (size_t)((freeB + have) * 0.6);
+    cap = std::min(cap, std::max<size_t>(budget / bytesPerPath(c->lights.size()), 65536));
+  }
+  return cap;
 }
 
 int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
@@ -415,11 +546,22 @@ int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
   if ((rc = syncLights(c))) return rc;
   if ((rc = syncTextures(c))) return rc;
   if (c->nOwned == 0) { c->launches += seeds.size(); return MOX_OK; }
-  size_t perBatch = std::max<size_t>(1, c->maxBatchPaths / c->nOwned);
+  size_t perBatch = std::max<size_t>(1, batchCap(c) / c->nOwned);
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
-  for (size_t i = 0; i < seeds.size(); i += perBatch) {
-    std::vector<int32_t> chunk(seeds.begin() + i, seeds.begin() + std::min(seeds.size(), i + perBatch));
-    if ((rc = renderBatch(c, chunk))) return rc;
+  for (size_t i = 0; i < seeds.size();) {
+    const size_t n = std::min(perBatch, seeds.size() - i);
+    std::vector<int32_t> chunk(seeds.begin() + i, seeds.begin() + i + n);
+    rc = renderBatch(c, chunk);
+    if (rc == MOX_ERR_OOM && perBatch > 1) {
+      // the allocation failed after all (fragmentation, another context on the device): free the wavefront
+      // state, halve the batch and render this chunk again (nothing of it was enqueued)
+      cudaGetLastError();
+      for (auto& sl : c->slices) { int32_t* sd = sl.pb.seeds; sl.pb.seeds = nullptr; freePaths(sl.pb); cudaFree(sd); }
+      perBatch = std::max<size_t>(1, perBatch / 2);
+      continue;
+    }
+    if (rc) return rc;
+    i += n;
   }
   CUCK(c, cudaEventRecord(c->ev1, c->stream));
   CUCK(c, cudaEventSynchronize(c->ev1));
@@ -463,13 +605,15 @@ int mox_create(mox_ctx** out, int device_id) {
   mox_ctx* c = new mox_ctx();
   c->device = device_id;
   if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)) != cudaSuccess) {
     std::string msg = cudaGetErrorString(e);
     delete c;
     return fail(nullptr, MOX_ERR_CUDA, msg);
   }
   if (const char* env = getenv("MOX_SORT_RAYS")) c->sortRays = atoi(env) != 0;
   if (const char* env = getenv("MOX_MAX_BATCH_PATHS")) { long long v = atoll(env); if (v > 0) c->maxBatchPaths = (size_t)v; }
+  if (const char* env = getenv("MOX_SLICES")) c->nSlices = std::min(std::max(atoi(env), 1), (int)mox_ctx::kMaxSlices);
   memset(&c->rp, 0, sizeof c->rp);
   c->rp.maxDepth = 256; c->rp.eps = 0.001f; c->rp.minIntensity = 0.001f;
   c->rp.bad = make_float3(1.f, 1.f, 1.f);
@@ -488,11 +632,18 @@ void mox_destroy(mox_ctx* c) {
   c->dTexObjs.release();
   c->buildArena.release();
   cudaFree(c->dNodes); cudaFree(c->dPacked); cudaFree(c->dNodes8); cudaFree(c->dPacked8); cudaFree(c->dAccu); cudaFree(c->dOwned);
-  freePaths(c->pb);
+  for (int k = 0; k < mox_ctx::kMaxSlices; ++k) {
+    mox_ctx::Slice& sl = c->slices[k];
+    if (sl.stream && k) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    freePaths(sl.pb);
+    sl.timer.release();
+    if (sl.evReady) cudaEventDestroy(sl.evReady);
+    if (sl.hostCnt) cudaFreeHost(sl.hostCnt);
+  }
   if (c->pinned) cudaFreeHost(c->pinned);
-  c->timer.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -595,7 +746,7 @@ int mox_add_mesh(mox_ctx* c, const float* v, size_t nv, const float* n, size_t n
                  const int32_t* nIdx, const int32_t* tIdx, size_t nFaces, int kind, const void* params, uint32_t* out_first) {
   if (!c) return MOX_ERR_INVALID;
   if (!params || (nFaces && (!v || !vIdx))) return fail(c, MOX_ERR_INVALID, "null argument");
-  if (c->prims.size() + nFaces >= (1u << 30)) return fail(c, MOX_ERR_INVALID, "too many primitives");
+  if (c->prims.size() + nFaces >= (1u << MOX_HIT_ID_BITS)) return fail(c, MOX_ERR_INVALID, "too many primitives");
   int m = addMaterial(c, kind, params);
   if (m < 0) return fail(c, MOX_ERR_INVALID, "bad material kind");
   bool hasN = nn > 0 && n && nIdx, hasT = nt > 0 && uv && tIdx;
@@ -769,7 +920,8 @@ int mox_set_accum(mox_ctx* c, const float* src, uint64_t launches) {
   if (!src || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
   int rc = bind(c);
   if (rc) return rc;
-  CUCK(c, cudaMemcpy(c->dAccu, src, (size_t)c->accuW * c->accuH * 12, cudaMemcpyHostToDevice));
+  CUCK(c, cudaMemcpyAsync(c->dAccu, src, (size_t)c->accuW * c->accuH * 12, cudaMemcpyHostToDevice, c->stream));
+  CUCK(c, cudaStreamSynchronize(c->stream));
   c->launches = launches;
   return MOX_OK;
 }
@@ -818,7 +970,7 @@ int mox_unpack_owned(mox_ctx* c, uint32_t rank, const void* dev_src) {
     std::vector<uint32_t> l;
     ownedList(c->rp.W, c->rp.H, c->tile, c->world, rank, l);
     if ((rc = ensure(c, b, l.size() * 4))) return rc;
-    if (!l.empty()) CUCK(c, cudaMemcpy(b.p, l.data(), l.size() * 4, cudaMemcpyHostToDevice));
+    if (!l.empty()) { CUCK(c, cudaMemcpyAsync(b.p, l.data(), l.size() * 4, cudaMemcpyHostToDevice, c->stream)); CUCK(c, cudaStreamSynchronize(c->stream)); }
     c->ownedCount[rank] = l.size();
   }
   launchUnpackOwned(c->dAccu, (const uint32_t*)b.p, (uint32_t)c->ownedCount[rank], (const float*)dev_src, c->stream);
@@ -864,7 +1016,7 @@ int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* d
   launchSplitRays((const float4*)dev_rays, (float4*)c->dQueryO.p, (float4*)c->dQueryD.p, n, c->stream);
   TraceJob job;
   job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n; job.countPtr = nullptr; job.originMod = 0;
-  job.cursor = counters + C_CURSOR; job.hits = (float4*)dev_hits; job.shC = nullptr; job.counters = counters;
+  job.cursor = counters + C_CURSOR; job.hits = (float4*)dev_hits; job.hits2 = nullptr; job.shC = nullptr; job.counters = counters;
   CUCK(c, cudaMemsetAsync(job.cursor, 0, 4, c->stream));
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
   launchTraverse(sceneView(c), job, false, count, c->stream);
@@ -893,7 +1045,9 @@ int mox_trace_closest(mox_ctx* c, const float* rays, size_t n, void* hits) {
   void *dRays = nullptr, *dHits = nullptr;
   CUCK(c, cudaMalloc(&dRays, n * 32));
   CUCK(c, cudaMalloc(&dHits, n * 16));
-  CUCK(c, cudaMemcpy(dRays, rays, n * 32, cudaMemcpyHostToDevice));
+  // stream-ordered: the traversal kernel runs on the (non-blocking) context stream
+  { cudaError_t e = cudaMemcpyAsync(dRays, rays, n * 32, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) { cudaFree(dRays); cudaFree(dHits); return fail(c, MOX_ERR_CUDA, cudaGetErrorString(e)); } }
   rc = mox_trace_closest_device(c, dRays, n, dHits, nullptr);
   if (!rc) {
     cudaError_t e = cudaMemcpy(hits, dHits, n * 16, cudaMemcpyDeviceToHost);
@@ -920,13 +1074,13 @@ int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
     return rc;
   }
   uint32_t* counters = (uint32_t*)c->dQueryCounters.p;
-  cudaMemcpy(dRays, rays, n * 32, cudaMemcpyHostToDevice);
+  cudaMemcpyAsync(dRays, rays, n * 32, cudaMemcpyHostToDevice, c->stream);   // stream-ordered, see mox_trace_closest
   cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream);
   launchSplitRays((const float4*)dRays, (float4*)c->dQueryO.p, (float4*)c->dQueryD.p, n, c->stream);
   launchFillOnes((float4*)dC, n, c->stream);
   TraceJob job;
   job.rayO = (const float4*)c->dQueryO.p; job.rayD = (const float4*)c->dQueryD.p; job.queue = nullptr; job.count = (uint32_t)n; job.countPtr = nullptr; job.originMod = 0;
-  job.cursor = counters + C_CURSOR; job.hits = nullptr; job.shC = (float4*)dC; job.counters = counters;
+  job.cursor = counters + C_CURSOR; job.hits = nullptr; job.hits2 = nullptr; job.shC = (float4*)dC; job.counters = counters;
   launchTraverse(sceneView(c), job, true, false, c->stream);
   launchCopyRgb((const float4*)dC, (float*)dOut, n, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -949,8 +1103,8 @@ extern "C" int mox_debug_radix_sort(mox_ctx* c, uint32_t* keys, uint32_t* vals, 
   uint32_t *dk = nullptr, *dv = nullptr;
   CUCK(c, cudaMalloc(&dk, n * 4));
   CUCK(c, cudaMalloc(&dv, n * 4));
-  CUCK(c, cudaMemcpy(dk, keys, n * 4, cudaMemcpyHostToDevice));
-  CUCK(c, cudaMemcpy(dv, vals, n * 4, cudaMemcpyHostToDevice));
+  CUCK(c, cudaMemcpyAsync(dk, keys, n * 4, cudaMemcpyHostToDevice, c->stream));
+  CUCK(c, cudaMemcpyAsync(dv, vals, n * 4, cudaMemcpyHostToDevice, c->stream));
   std::string err;
   bool ok = radixSortPairs(dk, dv, (int)n, c->stream, err);
   if (ok) {

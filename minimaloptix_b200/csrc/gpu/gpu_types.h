@@ -78,6 +78,20 @@ static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
 #define MOX_SHADOW_INVISIBLE 0u  // no any-hit program (lambertian, metal, glass, light)
 #define MOX_SHADOW_BLOCKS 1u     // Disney NORMAL
 #define MOX_SHADOW_TINTS 2u      // Disney GLASS: attenuation *= color
+// Which closest-hit program the primitive runs, bits 2..4 of the same word: the traversal kernel writes it into
+// the hit record, so classifying a hit needs no prims -> mats -> brdfType chain (three dependent loads).
+#define MOX_CLASS_LAMBERT 0u
+#define MOX_CLASS_METAL 1u
+#define MOX_CLASS_DIELECTRIC 2u  // glass, and Disney with brdfType GLASS
+#define MOX_CLASS_DISNEY 3u      // Disney NORMAL
+#define MOX_CLASS_LIGHT 4u
+#define MOX_CLASS_SHIFT 2
+// Hit record of the render path: (t, bits) with bits = primitive id | class << 28; -1 = miss; -2 = the path was
+// shaded and did not spawn a ray (nothing more to add).  Primitive ids are therefore limited to 2^28.
+#define MOX_HIT_ID_BITS 28
+#define MOX_HIT_ID_MASK 0x0fffffffu
+#define MOX_HIT_MISS (-1)
+#define MOX_HIT_DEAD (-2)
 
 // Per-triangle shading record, 128 bytes, indexed like `tris`:
 //   r0 = p0.xyz | flags (bit 0: has normals, bit 1: has uvs)     r1 = p1.xyz | uv0.x     r2 = p2.xyz | uv0.y

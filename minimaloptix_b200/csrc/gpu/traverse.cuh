@@ -101,7 +101,7 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
 //   * closest hit obeys the (t, id) lexicographic rule; any hit: Disney prims only, NORMAL
 //     blocks, GLASS tints (Material.cu:225-232);
 //   * per-lane traversal stack in local memory (far children only).
-template <bool ANYHIT, bool COUNT>
+template <bool ANYHIT, bool COUNT, bool CLASSIFY = false>
 __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const TraceJob& job) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -117,6 +117,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
   r.o = r.d = r.idir = mk3(0.f); r.tmin = 0.f;
   float tBest = 0.f, bBeta = 0.f, bGamma = 0.f;
   int bPrim = -1;
+  uint32_t bCls = 0;
   float3 atten = mk3(1.f);
   uint32_t nv = 0, np = 0;
 
@@ -223,6 +224,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
               }
             } else {
               tBest = t; bPrim = id; bBeta = be; bGamma = ga;
+              if (CLASSIFY) bCls = __float_as_uint(__ldg(&rec[1].w)) >> MOX_CLASS_SHIFT;   // shade class of the winner (k_pack)
             }
           }
           ++lk;
@@ -241,6 +243,8 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
             float4 c = job.shC[rayId];
             job.shC[rayId] = make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w);
           }
+        } else if (CLASSIFY) {
+          MOX_ST_STREAM(job.hits2 + rayId, make_float2(tBest, __int_as_float(bPrim < 0 ? MOX_HIT_MISS : (int)((uint32_t)bPrim | (bCls << MOX_HIT_ID_BITS)))));
         } else {
           MOX_ST_STREAM(job.hits + rayId, make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma));
         }

@@ -7,7 +7,8 @@
 //   rayO[id] = (origin, tmin)   rayD[id] = (direction, tmax); tmax < 0 marks an unused slot
 //   queue    : optional indirection, ray id = queue[i] for i < count
 //   cursor   : global fetch cursor, zeroed before the launch
-//   hits     : closest hit: hits[id] = (t, prim id as int bits or -1, beta, gamma)
+//   hits     : closest hit, raw query form: hits[id] = (t, prim id as int bits or -1, beta, gamma)
+//   hits2    : closest hit, render form (CLASSIFY kernels): hits2[id] = (t, prim id | class << 28, or -1)
 //   shC      : any hit: shC[id].xyz *= transmittance
 struct TraceJob {
   const float4* rayO;
@@ -18,6 +19,7 @@ struct TraceJob {
   uint32_t originMod;        // when non-zero, the origin of ray id is rayO[id % originMod]
   uint32_t* cursor;
   float4* hits;
+  float2* hits2;
   float4* shC;
   uint32_t* counters;
   int fetchThreshold;   // refill idle lanes when fewer than this many lanes are traversing

@@ -15,14 +15,44 @@
 
 #define MOX_WIDE_STACK MOX_TRAVERSAL_STACK
 
+// Quantised plane byte -> float.  I2F.U8 runs on the conversion pipe (15.4 results/clk/SM measured,
+// scripts/microbench/pipe_rates.cu, against 124 FFMA): 48 conversions per node step keep that pipe ~70 % busy
+// at today's node-step rate (both traversal kernels sit at the same 42.5 G node steps/s whatever their primitive
+// load).  MOX_BYTE_PRMT instead builds m = 1 + b * 2^-15 with one PRMT on the ALU pipe — byte b dropped into
+// mantissa bits 8..15 of 1.0f — and folds the affine map back into the plane FMA:
+//   b * ia + on  ==  m * (2^15 ia) + (on - 2^15 ia)
+// The addend's rounding error (<= 2^-24 of 2^15 |ia|, i.e. 2^-9 of one quantisation step) is added to the
+// conservative margin, so boxes only ever grow.
+#ifdef MOX_BYTE_PRMT
+// `one` is 1.0f's bit pattern held in a register (see traverseWidePersistent): with the constant as an immediate
+// ptxas needs the byte selector in a register and re-materialises four selectors per node.
+MOX_D float byteToFloat(uint32_t w, int i, uint32_t one) {
+  uint32_t r;
+  if (i == 0) asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(one));
+  else if (i == 1) asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(one));
+  else if (i == 2) asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(w), "r"(one));
+  else asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(one));
+  return __uint_as_float(r);
+}
+#define MOX_B2F(w, i) byteToFloat(w, i, one)
+#else
 MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+#define MOX_B2F(w, i) byteToFloat(w, i)
+#endif
 
-template <bool ANYHIT, bool COUNT>
+// CLASSIFY (closest hit of the render path): the hit record is (t, primitive id | shade class << 28) — the class
+// comes from the winning primitive's packed record — and beta / gamma are not carried (two registers less per
+// lane); the shade kernels recompute them from the same operands.  The raw query keeps the four-word record.
+template <bool ANYHIT, bool COUNT, bool CLASSIFY = false>
 __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const TraceJob& job) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
   const uint32_t jobCount = job.countPtr ? __ldg(job.countPtr) : job.count;
+#ifdef MOX_BYTE_PRMT
+  // 0x3f800000 that ptxas cannot fold into an immediate (a launch never has 2^31 rays)
+  const uint32_t one = 0x3f800000u | (job.count >> 31);
+#endif
   uint2 stack[MOX_WIDE_STACK];
   int sp = 0;
   uint32_t gBase = 0, gBits = 0;  // node group
@@ -32,6 +62,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   float3 o = mk3(0.f), d = mk3(0.f), idir = mk3(0.f);
   float tmin = 0.f, tBest = 0.f, bBeta = 0.f, bGamma = 0.f;
   int bPrim = -1;
+  uint32_t bCls = 0;
   float3 atten = mk3(1.f);
   uint32_t nv = 0, np = 0;
 
@@ -54,7 +85,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
               RayPre r = prepRay(mk3(ro), mk3(rd), ro.w);
               o = r.o; d = r.d; idir = r.idir; tmin = r.tmin;
               octinv = 7u ^ ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
-              tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
+              tBest = rd.w; bPrim = -1;
+              if (!CLASSIFY) { bBeta = 0.f; bGamma = 0.f; }
               atten = mk3(1.f);
               sp = 0;
               gBase = 0; gBits = 0x80000000u;  // root: one pending child, imask 0 -> node index 0
@@ -102,8 +134,23 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           // conservative: every axis gets its own rounding bound (2^-21 of the local origin term), folded
           // into separate near / far addends so the per-child cost stays one FMA per plane; the far side
           // is additionally widened by 1e-5 relative
+#ifdef MOX_BYTE_PRMT
+          const float kx = iax * 32768.f, ky = iay * 32768.f, kz = iaz * 32768.f;
+          const float ex_ = fmaf(2.384185791015625e-07f, fabsf(kx), 4.76837158203125e-07f * fabsf(oax));
+          const float ey_ = fmaf(2.384185791015625e-07f, fabsf(ky), 4.76837158203125e-07f * fabsf(oay));
+          const float ez_ = fmaf(2.384185791015625e-07f, fabsf(kz), 4.76837158203125e-07f * fabsf(oaz));
+          const float onx = (oax - ex_) - kx, ofx = (oax + ex_) - kx, ony = (oay - ey_) - ky, ofy = (oay + ey_) - ky;
+          const float onz = (oaz - ez_) - kz, ofz = (oaz + ez_) - kz;
+#define MOX_PLANE_SCALE_X kx
+#define MOX_PLANE_SCALE_Y ky
+#define MOX_PLANE_SCALE_Z kz
+#else
           const float ex_ = 4.76837158203125e-07f * fabsf(oax), ey_ = 4.76837158203125e-07f * fabsf(oay), ez_ = 4.76837158203125e-07f * fabsf(oaz);
           const float onx = oax - ex_, ofx = oax + ex_, ony = oay - ey_, ofy = oay + ey_, onz = oaz - ez_, ofz = oaz + ez_;
+#define MOX_PLANE_SCALE_X iax
+#define MOX_PLANE_SCALE_Y iay
+#define MOX_PLANE_SCALE_Z iaz
+#endif
           uint32_t hitmask = 0;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -121,9 +168,9 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
             const uint32_t nz = idir.z < 0.f ? qhz : qlz, fz = idir.z < 0.f ? qlz : qhz;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float tnx = fmaf(byteToFloat(nx, i), iax, onx), tfx = fmaf(byteToFloat(fx, i), iax, ofx);
-              const float tny = fmaf(byteToFloat(ny, i), iay, ony), tfy = fmaf(byteToFloat(fy, i), iay, ofy);
-              const float tnz = fmaf(byteToFloat(nz, i), iaz, onz), tfz = fmaf(byteToFloat(fz, i), iaz, ofz);
+              const float tnx = fmaf(MOX_B2F(nx, i), MOX_PLANE_SCALE_X, onx), tfx = fmaf(MOX_B2F(fx, i), MOX_PLANE_SCALE_X, ofx);
+              const float tny = fmaf(MOX_B2F(ny, i), MOX_PLANE_SCALE_Y, ony), tfy = fmaf(MOX_B2F(fy, i), MOX_PLANE_SCALE_Y, ofy);
+              const float tnz = fmaf(MOX_B2F(nz, i), MOX_PLANE_SCALE_Z, onz), tfz = fmaf(MOX_B2F(fz, i), MOX_PLANE_SCALE_Z, ofz);
               const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
               const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tBest)) * 1.00001f;
               // branch-free: an empty slot has count bits 0 (and an inverted box)
@@ -165,14 +212,16 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           if (hit) {
             if (ANYHIT) {
               // shadow class from the record itself (k_pack): only tinting glass still needs its material
-              const uint32_t cls = __float_as_uint(r1.w);
+              const uint32_t cls = __float_as_uint(r1.w) & 3u;
               if (cls == MOX_SHADOW_BLOCKS) { atten = mk3(0.f); tBits = 0u; gBits = 0u; sp = 0; }  // blocked: drop all pending work
               else if (cls == MOX_SHADOW_TINTS) {
                 const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
                 atten *= mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
               }
             } else {
-              tBest = t; bPrim = id; bBeta = be; bGamma = ga;
+              tBest = t; bPrim = id;
+              if (CLASSIFY) bCls = __float_as_uint(r1.w) >> MOX_CLASS_SHIFT;
+              else { bBeta = be; bGamma = ga; }
             }
           }
         }
@@ -192,6 +241,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
               float4 c = MOX_LD_STREAM(job.shC + rayId);
               MOX_ST_STREAM(job.shC + rayId, make_float4(c.x * atten.x, c.y * atten.y, c.z * atten.z, c.w));
             }
+          } else if (CLASSIFY) {
+            MOX_ST_STREAM(job.hits2 + rayId, make_float2(tBest, __int_as_float(bPrim < 0 ? MOX_HIT_MISS : (int)((uint32_t)bPrim | (bCls << MOX_HIT_ID_BITS)))));
           } else {
             MOX_ST_STREAM(job.hits + rayId, make_float4(tBest, __int_as_float(bPrim), bBeta, bGamma));
           }

@@ -5,9 +5,10 @@
 //   k_generate   camera()                      Camera.cu:21-36
 //   k_traverse   rtTrace: persistent-thread traversal, closest hit (extend rays) or shadow
 //                transmittance (disneyAnyHit, Material.cu:225-232) — traverse.cuh
-//   k_logic      miss (miss.cu:10-12), light() (Material.cu:238-240) and the depth test every
-//                scattering program starts with (Material.cu:29,50,73,119); surviving paths are
-//                binned into per-material queues
+//   k_classify   the depth test every scattering program starts with (Material.cu:29,50,73,119); surviving
+//                paths are binned into per-material queues by the shade class the traversal kernel left in
+//                the hit record.  Paths that end here — miss (miss.cu:10-12), light() (Material.cu:238-240),
+//                depth exceeded — are not touched again: k_accumulate adds their last term.
 //   k_shade_*    lambertian / metal / glass / disney   Material.cu:28-223, disney.h
 //   k_apply      adds the NEE terms to the path radiance in light order (deterministic)
 //   k_accumulate clamp + accuBuffer +=                 Camera.cu:39-41
@@ -84,59 +85,38 @@ constexpr int TRAV_TPB = 128;
 #define MOX_TRAV_MINBLOCKS 10  // caps the kernel at 48 registers: measured 983 (55 regs) -> 1022 Mrays/s; 12 blocks (40 regs): 1005
 #endif
 
-template <bool ANYHIT, bool COUNT>
+template <bool ANYHIT, bool COUNT, bool CLASSIFY>
 __global__ void __launch_bounds__(TRAV_TPB, MOX_TRAV_MINBLOCKS) k_traverse(SceneView s, TraceJob job) {
-  traverseWarpPersistent<ANYHIT, COUNT>(s, job);
+  traverseWarpPersistent<ANYHIT, COUNT, CLASSIFY>(s, job);
 }
 
 #ifndef MOX_WIDE_MINBLOCKS
 #define MOX_WIDE_MINBLOCKS 9   // 56 registers, no spills: measured 8 -> 1229, 9 -> 1258, 10 -> 1240 Mrays/s (before the weighted vote: 1064 / 1090 / 1069)
 #endif
-template <bool ANYHIT, bool COUNT>
+template <bool ANYHIT, bool COUNT, bool CLASSIFY>
 __global__ void __launch_bounds__(TRAV_TPB, MOX_WIDE_MINBLOCKS) k_traverse_wide(SceneView s, TraceJob job) {
-  traverseWidePersistent<ANYHIT, COUNT>(s, job);
+  traverseWidePersistent<ANYHIT, COUNT, CLASSIFY>(s, job);
 }
 
-// Consumes the closest-hit records of the current queue: miss (miss.cu:10-12), light
-// (Material.cu:238-240) and the depth test every scattering program starts with
-// (Material.cu:29,50,73,119) terminate the path here; the rest is binned by material.
-__global__ void __launch_bounds__(TPB) k_logic(LaunchCtx c, const uint32_t* __restrict__ queue, uint32_t count, uint32_t depth) {
+// Bins the paths of the current queue by the shade class in their hit record.  A miss, a light and a path
+// beyond rayMaxDepth end here without a write: their last term is added by k_accumulate from the same record.
+__global__ void __launch_bounds__(TPB) k_classify(LaunchCtx c, const uint32_t* __restrict__ queue, uint32_t count,
+                                                  const uint32_t* __restrict__ countPtr, uint32_t depth) {
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  if (countPtr) count = __ldg(countPtr);
   if (i >= count) return;
   uint32_t path = queue[i];
-  float4 h = c.pb.hit[path];
-  int prim = __float_as_int(h.y);
+  int bits = __float_as_int(c.pb.hit[path].y);
+  if (bits < 0) return;                                   // miss
+  uint32_t cls = (uint32_t)bits >> MOX_HIT_ID_BITS;
+  if (cls >= MOX_CLASS_LIGHT) return;                     // light(): terminal
   const RenderParams& rp = c.rp;
-  if (prim < 0) {  // miss: payload colour (1,1,1) * bgColor
-    float4 T = c.pb.thr[path], R = c.pb.rad[path];
-    float3 r = mk3(R) + mk3(T) * (mk3(1.f) * rp.bg);
-    c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
-    return;
-  }
-  PrimDesc pd = c.scene.prims[prim];
-  const GpuMaterial* m = c.scene.mats + (pd.typeMat >> 2);
-  int kind = __ldg(&m->kind);
-  if (kind == MOX_MAT_LIGHT) {
-    float4 T = c.pb.thr[path], R = c.pb.rad[path];
-    float3 r = mk3(R) + mk3(T) * f3(m->lgt.emission);
-    c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
-    return;
-  }
   // incoming payload colour is always (1,1,1): |colour| = sqrt(3)
-  if (depth > rp.maxDepth || length(mk3(1.f)) < rp.minIntensity) {
-    float4 T = c.pb.thr[path], R = c.pb.rad[path];
-    float3 r = mk3(R) + mk3(T) * rp.absorb;
-    c.pb.rad[path] = make_float4(r.x, r.y, r.z, 0.f);
-    return;
-  }
-  int q = kind == MOX_MAT_LAMBERTIAN ? Q_LAMBERT
-        : kind == MOX_MAT_METAL ? Q_METAL
-        : kind == MOX_MAT_GLASS ? Q_DIELECTRIC
-        : (m->dis.brdfType == GLASS ? Q_DIELECTRIC : Q_DISNEY);
-  // one warp-aggregated push per queue present in the warp
-  for (int k = 0; k < Q_COUNT; ++k) {
-    if (q == k) {
-      uint32_t pos = queuePush(c.pb.counters + C_MAT0 + k);
+  if (depth > rp.maxDepth || length(mk3(1.f)) < rp.minIntensity) return;   // absorbed
+  // one warp-aggregated push per queue present in the warp (classes 0..3 are the queue indices)
+  for (uint32_t k = 0; k < Q_COUNT; ++k) {
+    if (cls == k) {
+      uint32_t pos = queuePush(c.bc + C_MAT0 + k);
       c.pb.qMat[k][pos] = path;
     }
   }
@@ -147,9 +127,18 @@ struct Attr { float3 Ng, Ns, front, back, hitPoint; float u, v; };
 
 __device__ __forceinline__ float3 ld3(const float* p, int i) { return mk3(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
 
+// beta / gamma of a triangle hit are not stored by the traversal kernel: they are recomputed here with the
+// operation sequence of the primitive test (triTest) on the same operands — bit-identical values.
+__device__ __forceinline__ void triBarycentrics(const float3& o, const float3& d, const float3& p0, const float3& p1, const float3& p2,
+                                                float& beta, float& gamma) {
+  float t;
+  triTest(o, d, 0.f, p0, p1 - p0, p0 - p2, t, beta, gamma);
+}
+
 __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc& pd, const float3& o, const float3& d,
-                                               float t, float beta, float gamma, bool needShading) {
+                                               float t, bool needShading) {
   Attr a;
+  float beta = 0.f, gamma = 0.f;
   uint32_t type = pd.typeMat & 3u;
   a.hitPoint = o + t * d;
   a.u = a.v = 0.f;
@@ -174,6 +163,7 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
       const uint32_t flags = __float_as_uint(r0.w);
       if (flags) {
         const float4 r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
+        triBarycentrics(o, d, p0, p1, p2, beta, gamma);
         if (flags & 1u) a.Ns = normalize(mk3(r4) * beta + mk3(r5) * gamma + mk3(r3) * (1.f - beta - gamma));
         if (flags & 2u) {
           float w = 1.0f - beta - gamma;
@@ -193,6 +183,7 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
     a.front = a.back = a.hitPoint;
     if (needShading) {
       int n0 = __ldg(&ti->n[0]);
+      if (n0 >= 0 || __ldg(&ti->t[0]) >= 0) triBarycentrics(o, d, p0, p1, p2, beta, gamma);
       if (n0 >= 0) {
         int n1 = __ldg(&ti->n[1]), n2 = __ldg(&ti->n[2]);
         a.Ns = normalize(ld3(s.normals, n1) * beta + ld3(s.normals, n2) * gamma + ld3(s.normals, n0) * (1.f - beta - gamma));
@@ -221,7 +212,7 @@ template <int RM>
 struct ShadeIn {
   uint32_t path;
   float3 o, d;
-  float t, beta, gamma;
+  float t;
   PrimDesc pd;
   const GpuMaterial* m;
   RngT<RM> rng;
@@ -231,10 +222,11 @@ template <int RM>
 __device__ __forceinline__ ShadeIn<RM> loadShadeIn(const LaunchCtx& c, uint32_t path, uint32_t depth) {
   ShadeIn<RM> s;
   s.path = path;
-  float4 ro = c.pb.rayO[path], rd = c.pb.rayD[path], h = c.pb.hit[path];
+  float4 ro = c.pb.rayO[path], rd = c.pb.rayD[path];
+  float2 h = c.pb.hit[path];
   s.o = mk3(ro); s.d = mk3(rd);
-  s.t = h.x; s.beta = h.z; s.gamma = h.w;
-  s.pd = c.scene.prims[__float_as_int(h.y)];
+  s.t = h.x;
+  s.pd = c.scene.prims[__float_as_uint(h.y) & MOX_HIT_ID_MASK];
   s.m = c.scene.mats + (s.pd.typeMat >> 2);
   if (RM == 0) {
     s.rng = makeRng<RM>(c.pb.state[path], 0u, 0u, depth);
@@ -253,7 +245,7 @@ __device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const f
   float3 t = mk3(T) * A;
   c.pb.thr[path] = make_float4(t.x, t.y, t.z, 0.f);
   c.pb.state[path] = childState;
-  uint32_t pos = queuePush(c.pb.counters + C_NEXT);
+  uint32_t pos = queuePush(c.bc + C_NEXT);
   c.pb.qNext[pos] = path;
   if (c.pb.qKey) {
     // reordering key: 21-bit Morton cell of the origin (7 bits/axis of the scene box) | direction octant
@@ -273,7 +265,7 @@ __global__ void __launch_bounds__(TPB) k_shade_diffuse(LaunchCtx c, uint32_t cou
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
   ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[METAL ? Q_METAL : Q_LAMBERT][i], depth);
-  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, false);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, false);
   float3 v = randInUnitSphere(s.rng);
   float3 dir, albedo;
   if (METAL) {
@@ -292,7 +284,7 @@ __global__ void __launch_bounds__(TPB) k_shade_dielectric(LaunchCtx c, uint32_t 
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
   ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DIELECTRIC][i], depth);
-  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, true);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, true);
   float ior;
   float3 tint;
   if (s.m->kind == MOX_MAT_GLASS) { ior = s.m->gls.refIdx; tint = f3(s.m->gls.albedo); }
@@ -323,7 +315,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
   if (i >= count) return;
   ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DISNEY][i], depth);
-  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, s.beta, s.gamma, true);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, true);
   const DisneyParams dp = s.m->dis;
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
@@ -367,7 +359,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
     c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
     if (trace) {
       c.pb.shD[slot] = make_float4(L.x, L.y, L.z, lightDst - c.rp.eps);
-      uint32_t pos = queuePush(c.pb.counters + C_SHQ);
+      uint32_t pos = queuePush(c.bc + C_SHQ);
       c.pb.shQueue[pos] = (uint32_t)slot;
     }
   }
@@ -381,13 +373,17 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
     }
   }
   disneySample(s.rng, dp, N, L, V, H);
+  bool spawned = false;
   if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
     float pdf = dh.pdf(L, H);
     if (pdf > 0) {
       float3 brdf = dh.eval(L, V, H);
       spawn(c, s.path, a.front, L, brdf / pdf, s.rng.forkState((int)depth + 1));
+      spawned = true;
     }
   }
+  // no indirect ray: the path ends with what it has; its (stale) hit record must not be read as a terminal hit
+  if (!spawned) c.pb.hit[s.path].y = __int_as_float(MOX_HIT_DEAD);
 }
 
 __global__ void __launch_bounds__(TPB) k_apply(LaunchCtx c, uint32_t count) {
@@ -411,7 +407,24 @@ __global__ void __launch_bounds__(TPB) k_accumulate(LaunchCtx c, uint32_t nSampl
   float3 acc = mk3(a[0], a[1], a[2]);
   uint32_t bad = 0;
   for (uint32_t s = 0; s < nSamples; ++s) {
-    float4 r = c.pb.rad[(size_t)s * c.nOwned + j];
+    const size_t p = (size_t)s * c.nOwned + j;
+    float4 r = c.pb.rad[p];
+    {
+      // The path's last term.  Its final hit record says how it ended: miss -> payload colour (1,1,1) * bgColor
+      // (miss.cu:10-12); a light -> emission (Material.cu:238-240); a scattering material -> the depth test failed,
+      // absorbColor (Material.cu:29,50,73,119); MOX_HIT_DEAD -> shaded without an indirect ray, nothing to add.
+      const int bits = __float_as_int(c.pb.hit[p].y);
+      if (bits != MOX_HIT_DEAD) {
+        float3 B;
+        if (bits < 0) B = mk3(1.f) * c.rp.bg;
+        else if (((uint32_t)bits >> MOX_HIT_ID_BITS) >= MOX_CLASS_LIGHT) {
+          const GpuMaterial* m = c.scene.mats + (__ldg(&c.scene.prims[(uint32_t)bits & MOX_HIT_ID_MASK].typeMat) >> 2);
+          B = mk3(__ldg(&m->lgt.emission.x), __ldg(&m->lgt.emission.y), __ldg(&m->lgt.emission.z));
+        } else B = c.rp.absorb;
+        const float3 rr = mk3(r) + mk3(c.pb.thr[p]) * B;
+        r = make_float4(rr.x, rr.y, rr.z, 0.f);
+      }
+    }
     if (!isfinite(r.x) || !isfinite(r.y) || !isfinite(r.z)) {
       // The reference paints badColor when a launch index raises an OptiX exception (Exception.cu:10-12,
       // MinimalOptiX.cpp:149-151).  A NaN/Inf sample is this path's exception: badColor instead of the
@@ -525,33 +538,35 @@ static int fetchThreshold(bool anyHit) {
   return t[anyHit ? 1 : 0];
 }
 
-template <bool ANYHIT, bool COUNT>
+template <bool ANYHIT, bool COUNT, bool CLASSIFY>
 static void launchTraverseT(const SceneView& s, const TraceJob& job, cudaStream_t stream) {
   static int bpsBinary = 0, bpsWide = 0;
-  if (s.nodes8) k_traverse_wide<ANYHIT, COUNT><<<persistentGridFor(k_traverse_wide<ANYHIT, COUNT>, job.count, bpsWide), TRAV_TPB, 0, stream>>>(s, job);
-  else k_traverse<ANYHIT, COUNT><<<persistentGridFor(k_traverse<ANYHIT, COUNT>, job.count, bpsBinary), TRAV_TPB, 0, stream>>>(s, job);
+  if (s.nodes8) k_traverse_wide<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse_wide<ANYHIT, COUNT, CLASSIFY>, job.count, bpsWide), TRAV_TPB, 0, stream>>>(s, job);
+  else k_traverse<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse<ANYHIT, COUNT, CLASSIFY>, job.count, bpsBinary), TRAV_TPB, 0, stream>>>(s, job);
 }
 
-void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool count, cudaStream_t stream) {
+void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool count, cudaStream_t stream, bool classify) {
   if (!jobIn.count) return;
   TraceJob job = jobIn;
   job.fetchThreshold = fetchThreshold(anyHit);
   cudaMemsetAsync(job.cursor, 0, 4, stream);
-  if (anyHit && count) launchTraverseT<true, true>(s, job, stream);
-  else if (anyHit) launchTraverseT<true, false>(s, job, stream);
-  else if (count) launchTraverseT<false, true>(s, job, stream);
-  else launchTraverseT<false, false>(s, job, stream);
+  if (anyHit && count) launchTraverseT<true, true, false>(s, job, stream);
+  else if (anyHit) launchTraverseT<true, false, false>(s, job, stream);
+  else if (classify && count) launchTraverseT<false, true, true>(s, job, stream);
+  else if (classify) launchTraverseT<false, false, true>(s, job, stream);
+  else if (count) launchTraverseT<false, true, false>(s, job, stream);
+  else launchTraverseT<false, false, false>(s, job, stream);
 }
 
-void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
+void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, const uint32_t* countPtr, uint32_t depth) {
   if (!count) return;
   TraceJob job;
-  job.rayO = c.pb.rayO; job.rayD = c.pb.rayD; job.queue = queue; job.count = count; job.countPtr = nullptr; job.originMod = 0;
-  job.cursor = c.pb.counters + C_CURSOR; job.hits = c.pb.hit; job.shC = nullptr; job.counters = c.pb.counters;
-  launchTraverse(c.scene, job, false, c.countTraversal, c.stream);
+  job.rayO = c.pb.rayO; job.rayD = c.pb.rayD; job.queue = queue; job.count = count; job.countPtr = countPtr; job.originMod = 0;
+  job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.hits2 = c.pb.hit; job.shC = nullptr; job.counters = c.pb.counters;
+  launchTraverse(c.scene, job, false, c.countTraversal, c.stream, true);
 }
-void launchLogic(const LaunchCtx& c, const uint32_t* queue, uint32_t count, uint32_t depth) {
-  if (count) k_logic<<<grid(count), TPB, 0, c.stream>>>(c, queue, count, depth);
+void launchClassify(const LaunchCtx& c, const uint32_t* queue, uint32_t count, const uint32_t* countPtr, uint32_t depth) {
+  if (count) k_classify<<<grid(count), TPB, 0, c.stream>>>(c, queue, count, countPtr, depth);
 }
 void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
   if (!count) return;
@@ -581,8 +596,8 @@ void launchShadow(const LaunchCtx& c, uint32_t disneyCount) {
   TraceJob job;
   // dense queue of the slots that need a ray; its length lives in device memory (no host sync)
   job.rayO = c.pb.shO; job.rayD = c.pb.shD; job.queue = c.pb.shQueue; job.count = (uint32_t)slots;
-  job.countPtr = c.pb.counters + C_SHQ; job.originMod = disneyCount;
-  job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
+  job.countPtr = c.bc + C_SHQ; job.originMod = disneyCount;
+  job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.hits2 = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
   launchTraverse(c.scene, job, true, c.countTraversal, c.stream);
 }
 void launchApply(const LaunchCtx& c, uint32_t disneyCount) {

@@ -1,8 +1,11 @@
-#!/usr/bin/env python3
-import json, sys
-d = json.load(open(sys.argv[1]))
-for k in ("roofline_closest", "roofline_shadow"):
-    r = d.get(k)
-    if r:
-        print(k, {x: (round(r[x], 3) if isinstance(r[x], float) else r[x]) for x in ("achieved", "frac", "traffic", "bytes_per_ray", "nodes_per_ray", "prims_per_ray", "rays_per_s", "share_of_step")})
-print("value", d["value"], "e2e", d["e2e"], "cpu", d.get("cpu_baseline"), "stage", d["stage_ms"])
+#!/usr/bin/env python
+"""One-line summary of a bench.py JSON line (A/B runs)."""
+import json
+import sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    st = d.get("stage_ms", {})
+    print(sys.argv[2] if len(sys.argv) > 2 else "", "value %.1f" % d["value"], "ms/step %.2f" % d["ms_per_step"], "e2e %.1f" % d["e2e"]["value"],
+          "stages", {k[3:]: round(v, 1) for k, v in st.items()}, "launches", d.get("gpu_launches"), "clk", d.get("clocks", {}).get("sm_mhz"))
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e)
