@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MOX_ABI_VERSION 1
+#define MOX_ABI_VERSION 2
 
 typedef struct mox_ctx mox_ctx; /* opaque */
 
@@ -196,6 +196,40 @@ int mox_pack_owned(mox_ctx*, void* dev_dst);
 int mox_unpack_owned(mox_ctx*, uint32_t rank, const void* dev_src);
 
 int mox_get_stats(mox_ctx*, mox_stats*);
+
+/* ---- multi-GPU inside the library ------------------------------------------ */
+
+/* One handle that renders on several GPUs of this process (the reference has a single
+ * optix::Context on one device, MinimalOptiX.cpp:131; OptiX itself would take
+ * context->setDevices()).  The scene calls are replicated to every device, the image is
+ * tile-split (rank i of n, mox_set_partition), build and launch run one host thread per
+ * device, and a read-back gathers the tiles over NVLink: every device writes the pixels it
+ * owns DIRECTLY into device 0's gather buffer (peer stores, no staging, no collective).
+ * Every other entry point of this header works on the returned handle unchanged;
+ * mox_set_partition / mox_owned_pixels / mox_pack_owned / mox_unpack_owned are refused.
+ * n_devices == 1 is allowed. */
+int mox_create_multi(mox_ctx** out, const int* device_ids, int n_devices);
+int mox_device_count(const mox_ctx*);   /* 1 for a plain context */
+
+/* Asynchronous accuBuffer->map(): _begin snapshots the accumulation buffer (for a multi-GPU
+ * handle: gathers the tiles) and starts the device->host copy on a copy stream; rendering
+ * may continue.  _end waits for that copy; *out (W*H*3 floats, row 0 = bottom) stays valid
+ * until the second next _begin (two buffers alternate).  mox_read_accum / mox_map_accum are
+ * _begin + _end. */
+int mox_read_accum_begin(mox_ctx*);
+int mox_read_accum_end(mox_ctx*, const float** out);
+
+/* Cross-process tile exchange over peer memory (one process per GPU, e.g. under torchrun):
+ * rank 0 exports its two gather buffers as CUDA IPC handles (64 bytes each), the other
+ * ranks import them once; per frame every rank — rank 0 included — pushes the pixels it
+ * owns into buffer `which` with direct NVLink stores (synchronous on return), the caller
+ * runs a barrier, and rank 0 reads the frame with mox_read_gathered_begin/_end. */
+#define MOX_IPC_HANDLE_BYTES 64
+int mox_gather_export(mox_ctx*, int which, void* handle_out);
+int mox_gather_import(mox_ctx*, int which, const void* handle);
+int mox_gather_push(mox_ctx*, int which);
+int mox_read_gathered_begin(mox_ctx*, int which);
+int mox_read_gathered_end(mox_ctx*, int which, const float** out);
 
 /* ---- raw ray queries (BASELINE config 5, primitive-id parity) -------------- */
 

@@ -47,11 +47,20 @@ SIGNATURES = {
     "pack_owned": (C.c_int, [_vp, _vp]),
     "unpack_owned": (C.c_int, [_vp, _u32, _vp]),
     "get_stats": (C.c_int, [_vp, C.POINTER(S.Stats)]),
+    "device_count": (C.c_int, [_vp]),
+    "read_accum_begin": (C.c_int, [_vp]),
+    "read_accum_end": (C.c_int, [_vp, C.POINTER(_fp)]),
     "trace_closest": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "trace_shadow": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
 }
 # Only the GPU library has the device-pointer query.
-GPU_ONLY = {"trace_closest_device": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.POINTER(_f32)]),
+GPU_ONLY = {"create_multi": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int]),
+            "gather_export": (C.c_int, [_vp, C.c_int, _vp]),
+            "gather_import": (C.c_int, [_vp, C.c_int, _vp]),
+            "gather_push": (C.c_int, [_vp, C.c_int]),
+            "read_gathered_begin": (C.c_int, [_vp, C.c_int]),
+            "read_gathered_end": (C.c_int, [_vp, C.c_int, C.POINTER(_fp)]),
+            "trace_closest_device": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.POINTER(_f32)]),
             "debug_radix_sort": (C.c_int, [_vp, _vp, _vp, C.c_size_t])}
 
 
@@ -77,6 +86,10 @@ class Backend:
     def context(self, device=0):
         return Context(self, device)
 
+    def multi_context(self, devices):
+        """One handle rendering on several GPUs of this process (mox_create_multi)."""
+        return Context(self, list(devices))
+
 
 def _f32c(a):
     return np.ascontiguousarray(a, dtype=np.float32)
@@ -96,7 +109,11 @@ class Context:
     def __init__(self, backend, device=0):
         self.b = backend
         self.h = _vp()
-        rc = backend.create(C.byref(self.h), device)
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*device)
+            rc = backend.create_multi(C.byref(self.h), ids, len(device))
+        else:
+            rc = backend.create(C.byref(self.h), device)
         if rc != 0:
             raise MoxError(f"{backend.prefix}create failed ({rc}): {backend.last_error(None).decode()}")
         self.width = self.height = 0
@@ -197,6 +214,40 @@ class Context:
         """Zero-copy view (H, W, 3) of the pinned host copy; valid until the next map/read."""
         p = _fp()
         self._ck(self.b.map_accum(self.h, C.byref(p)), "map_accum")
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))
+
+    def read_accum_begin(self):
+        """Start the asynchronous read-back (snapshot / multi-GPU gather + device->host copy)."""
+        self._ck(self.b.read_accum_begin(self.h), "read_accum_begin")
+
+    def read_accum_end(self):
+        """Wait for the read-back started last; zero-copy (H, W, 3) view of the pinned host image."""
+        p = _fp()
+        self._ck(self.b.read_accum_end(self.h, C.byref(p)), "read_accum_end")
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))
+
+    def device_count(self):
+        return self.b.device_count(self.h)
+
+    # -- peer-memory tile gather across processes (one process per GPU)
+    def gather_export(self, which):
+        buf = C.create_string_buffer(64)
+        self._ck(self.b.gather_export(self.h, which, C.cast(buf, _vp)), "gather_export")
+        return buf.raw
+
+    def gather_import(self, which, handle):
+        buf = C.create_string_buffer(handle, 64)
+        self._ck(self.b.gather_import(self.h, which, C.cast(buf, _vp)), "gather_import")
+
+    def gather_push(self, which):
+        self._ck(self.b.gather_push(self.h, which), "gather_push")
+
+    def read_gathered_begin(self, which):
+        self._ck(self.b.read_gathered_begin(self.h, which), "read_gathered_begin")
+
+    def read_gathered_end(self, which):
+        p = _fp()
+        self._ck(self.b.read_gathered_end(self.h, which, C.byref(p)), "read_gathered_end")
         return np.ctypeslib.as_array(p, shape=(self.height, self.width, 3))
 
     def set_accum(self, accum, launches):

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "build.h"
+#include "group.h"
 #include "mox.h"
 #include "rng.cuh"
 #include "wavefront.h"
@@ -119,6 +120,19 @@ struct mox_ctx {
   int nSlices = 2;
   float* pinned = nullptr;
   size_t pinnedBytes = 0;
+
+  // Gather / asynchronous read-back: two full-size device buffers (targets of the tile pushes, possibly of other
+  // GPUs), two pinned host images, a copy stream.  gatherPeer[w]: buffer w belongs to another rank (imported).
+  float* dGather[2] = {nullptr, nullptr};
+  int gatherPeer[2] = {0, 0};   // 0 own, 1 imported over CUDA IPC, 2 borrowed from another context of this process
+  float* hostGather[2] = {nullptr, nullptr};
+  size_t gatherBytes = 0;
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evPushed = nullptr, evCopied[2] = {nullptr, nullptr};
+  int readCur = 0;            // buffer the next mox_read_accum_begin uses
+  int readPending = -1;       // buffer of the begin that has not been ended yet
+
+  mox_group* group = nullptr; // set on the shell handle mox_create_multi returns
 
   // stats
   uint64_t raysPrimary = 0, raysBounce = 0, raysShadow = 0, nonfinite = 0, launches = 0, nodeVisits = 0, primTests = 0;
@@ -571,6 +585,37 @@ int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
   return MOX_OK;
 }
 
+void freeGather(mox_ctx* c) {
+  for (int w = 0; w < 2; ++w) {
+    if (c->dGather[w]) { if (c->gatherPeer[w] == 1) cudaIpcCloseMemHandle(c->dGather[w]); else if (!c->gatherPeer[w]) cudaFree(c->dGather[w]); }
+    if (c->hostGather[w]) cudaFreeHost(c->hostGather[w]);
+    c->dGather[w] = nullptr; c->hostGather[w] = nullptr; c->gatherPeer[w] = 0;
+  }
+  c->gatherBytes = 0; c->readPending = -1;
+}
+
+// The two gather buffers of this context (allocated on first use, re-allocated when the image size changes).
+int ensureGather(mox_ctx* c, bool hostSide) {
+  if (!c->dAccu) return fail(c, MOX_ERR_STATE, "no accumulation buffer (mox_set_globals first)");
+  const size_t bytes = (size_t)c->accuW * c->accuH * 12;
+  if (c->gatherBytes != bytes) {
+    cudaStreamSynchronize(c->stream);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    bool peer = c->gatherPeer[0] || c->gatherPeer[1];
+    if (peer && c->gatherBytes) return fail(c, MOX_ERR_STATE, "image size changed after mox_gather_import");
+    if (!peer) freeGather(c);
+    c->gatherBytes = bytes;
+  }
+  if (!c->copyStream) CUCK(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+  if (!c->evPushed) CUCK(c, cudaEventCreateWithFlags(&c->evPushed, cudaEventDisableTiming));
+  for (int w = 0; w < 2; ++w) {
+    if (!c->evCopied[w]) CUCK(c, cudaEventCreateWithFlags(&c->evCopied[w], cudaEventDisableTiming));
+    if (!c->dGather[w]) { CUCK(c, cudaMalloc(&c->dGather[w], bytes)); CUCK(c, cudaMemsetAsync(c->dGather[w], 0, bytes, c->stream)); }
+    if (hostSide && !c->hostGather[w]) CUCK(c, cudaMallocHost(&c->hostGather[w], bytes));
+  }
+  return MOX_OK;
+}
+
 int ensurePinned(mox_ctx* c, size_t bytes) {
   if (c->pinnedBytes >= bytes) return MOX_OK;
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -582,9 +627,53 @@ int ensurePinned(mox_ctx* c, size_t bytes) {
 
 }  // namespace
 
+// A multi-GPU handle (mox_create_multi) is a shell: every call is forwarded to its per-device contexts.
+#define GROUP_EACH(c, expr)                                                                      \
+  do {                                                                                           \
+    if ((c)->group) {                                                                            \
+      int rc_ = groupEach((c)->group, [&](mox_ctx* k, int) { return (expr); });                  \
+      if (rc_) (c)->err = groupError((c)->group);                                                \
+      return rc_;                                                                                \
+    }                                                                                            \
+  } while (0)
+#define GROUP_PAR(c, expr)                                                                       \
+  do {                                                                                           \
+    if ((c)->group) {                                                                            \
+      int rc_ = groupParallel((c)->group, [&](mox_ctx* k, int) { return (expr); });              \
+      if (rc_) (c)->err = groupError((c)->group);                                                \
+      return rc_;                                                                                \
+    }                                                                                            \
+  } while (0)
+#define GROUP_REFUSE(c, what) \
+  do { if ((c)->group) return fail((c), MOX_ERR_INVALID, what " is managed by the multi-GPU handle itself"); } while (0)
+#define GROUP_FIRST(c, expr)                                                                     \
+  do {                                                                                           \
+    if ((c)->group) {                                                                            \
+      mox_ctx* k = groupChild((c)->group, 0);                                                    \
+      int rc_ = (expr);                                                                          \
+      if (rc_) (c)->err = mox_last_error(k);                                                     \
+      return rc_;                                                                                \
+    }                                                                                            \
+  } while (0)
+
 extern "C" {
 
 int mox_abi_version(void) { return MOX_ABI_VERSION; }
+
+int mox_create_multi(mox_ctx** out, const int* device_ids, int n_devices) {
+  if (!out) return fail(nullptr, MOX_ERR_INVALID, "null out pointer");
+  *out = nullptr;
+  std::string err;
+  mox_group* g = nullptr;
+  int rc = groupCreate(&g, device_ids, n_devices, err);
+  if (rc) return fail(nullptr, rc, err);
+  mox_ctx* shell = new mox_ctx();
+  shell->group = g;
+  *out = shell;
+  return MOX_OK;
+}
+
+int mox_device_count(const mox_ctx* c) { return c ? (c->group ? groupCount(c->group) : 1) : 0; }
 
 const char* mox_last_error(const mox_ctx* c) { return c ? c->err.c_str() : g_createError.c_str(); }
 
@@ -623,6 +712,7 @@ int mox_create(mox_ctx** out, int device_id) {
 
 void mox_destroy(mox_ctx* c) {
   if (!c) return;
+  if (c->group) { groupDestroy(c->group); delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dShadeRec, &c->dQueryO,
@@ -641,6 +731,10 @@ void mox_destroy(mox_ctx* c) {
     if (sl.hostCnt) cudaFreeHost(sl.hostCnt);
   }
   if (c->pinned) cudaFreeHost(c->pinned);
+  freeGather(c);
+  if (c->copyStream) cudaStreamDestroy(c->copyStream);
+  if (c->evPushed) cudaEventDestroy(c->evPushed);
+  for (auto e : c->evCopied) if (e) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->evFork) cudaEventDestroy(c->evFork);
@@ -651,6 +745,7 @@ void mox_destroy(mox_ctx* c) {
 int mox_set_globals(mox_ctx* c, uint32_t width, uint32_t height, uint32_t rayMaxDepth, float rayEpsilonT, float rayMinIntensity,
                     const float absorbColor[3], const float badColor[3], const float bgColor[3]) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_set_globals(k, width, height, rayMaxDepth, rayEpsilonT, rayMinIntensity, absorbColor, badColor, bgColor));
   if (!width || !height || !absorbColor || !badColor || !bgColor) return fail(c, MOX_ERR_INVALID, "bad globals");
   if ((uint64_t)width * height > 0x7fffffffull / 3) return fail(c, MOX_ERR_INVALID, "image too large");
   int rc = bind(c);
@@ -675,6 +770,7 @@ int mox_set_globals(mox_ctx* c, uint32_t width, uint32_t height, uint32_t rayMax
 
 int mox_set_camera(mox_ctx* c, const CamParams* cam) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_set_camera(k, cam));
   if (!cam) return fail(c, MOX_ERR_INVALID, "null camera");
   c->rp.cam = *cam;
   c->haveCamera = true;
@@ -683,6 +779,7 @@ int mox_set_camera(mox_ctx* c, const CamParams* cam) {
 
 int mox_set_rng_mode(mox_ctx* c, int mode) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_set_rng_mode(k, mode));
   if (mode != MOX_RNG_REF && mode != MOX_RNG_PHILOX) return fail(c, MOX_ERR_INVALID, "bad rng mode");
   c->rp.rngMode = mode;
   return MOX_OK;
@@ -690,6 +787,7 @@ int mox_set_rng_mode(mox_ctx* c, int mode) {
 
 int mox_set_partition(mox_ctx* c, uint32_t rank, uint32_t world, uint32_t tile) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile partition");
   if (!world || rank >= world || !tile) return fail(c, MOX_ERR_INVALID, "bad partition");
   c->rank = rank; c->world = world; c->tile = tile;
   c->ownedDirty = true;
@@ -698,6 +796,7 @@ int mox_set_partition(mox_ctx* c, uint32_t rank, uint32_t world, uint32_t tile) 
 
 int mox_add_texture_rgba32f(mox_ctx* c, const float* texels, int w, int h, int* out_id) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_add_texture_rgba32f(k, texels, w, h, out_id));
   if (!texels || w <= 0 || h <= 0 || w > 32768 || h > 32768) return fail(c, MOX_ERR_INVALID, "bad texture");
   mox_ctx::HostTexture t;
   t.w = w; t.h = h;
@@ -710,6 +809,7 @@ int mox_add_texture_rgba32f(mox_ctx* c, const float* texels, int w, int h, int* 
 
 int mox_add_sphere(mox_ctx* c, const SphereParams* s, int kind, const void* params, uint32_t* out_id) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_add_sphere(k, s, kind, params, out_id));
   if (!s || !params) return fail(c, MOX_ERR_INVALID, "null argument");
   int m = addMaterial(c, kind, params);
   if (m < 0) return fail(c, MOX_ERR_INVALID, "bad material kind");
@@ -726,6 +826,7 @@ int mox_add_sphere(mox_ctx* c, const SphereParams* s, int kind, const void* para
 
 int mox_add_quad(mox_ctx* c, const QuadParams* q, int kind, const void* params, uint32_t* out_id) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_add_quad(k, q, kind, params, out_id));
   if (!q || !params) return fail(c, MOX_ERR_INVALID, "null argument");
   int m = addMaterial(c, kind, params);
   if (m < 0) return fail(c, MOX_ERR_INVALID, "bad material kind");
@@ -745,6 +846,7 @@ int mox_add_quad(mox_ctx* c, const QuadParams* q, int kind, const void* params, 
 int mox_add_mesh(mox_ctx* c, const float* v, size_t nv, const float* n, size_t nn, const float* uv, size_t nt, const int32_t* vIdx,
                  const int32_t* nIdx, const int32_t* tIdx, size_t nFaces, int kind, const void* params, uint32_t* out_first) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_add_mesh(k, v, nv, n, nn, uv, nt, vIdx, nIdx, tIdx, nFaces, kind, params, out_first));
   if (!params || (nFaces && (!v || !vIdx))) return fail(c, MOX_ERR_INVALID, "null argument");
   if (c->prims.size() + nFaces >= (1u << MOX_HIT_ID_BITS)) return fail(c, MOX_ERR_INVALID, "too many primitives");
   int m = addMaterial(c, kind, params);
@@ -778,6 +880,7 @@ int mox_add_mesh(mox_ctx* c, const float* v, size_t nv, const float* n, size_t n
 
 int mox_set_lights(mox_ctx* c, const LightParams* l, size_t n) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_set_lights(k, l, n));
   if (n && !l) return fail(c, MOX_ERR_INVALID, "null lights");
   c->lights.assign(l, l + n);
   c->lightsDirty = true;
@@ -786,6 +889,7 @@ int mox_set_lights(mox_ctx* c, const LightParams* l, size_t n) {
 
 int mox_clear_scene(mox_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_clear_scene(k));
   c->prims.clear(); c->tris.clear(); c->verts.clear(); c->normals.clear(); c->uvs.clear(); c->analytic.clear();
   c->mats.clear(); c->lights.clear();
   c->textures.clear(); c->texturesDirty = true;
@@ -796,6 +900,13 @@ int mox_clear_scene(mox_ctx* c) {
 
 int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   if (!c) return MOX_ERR_INVALID;
+  if (c->group) {
+    std::vector<float> ms(groupCount(c->group), 0.f);
+    int rc_ = groupParallel(c->group, [&](mox_ctx* k, int i) { return mox_build_accel(k, flags, &ms[i]); });
+    if (rc_) { c->err = groupError(c->group); return rc_; }
+    if (out_ms) *out_ms = *std::max_element(ms.begin(), ms.end());
+    return MOX_OK;
+  }
   int rc = bind(c);
   if (rc) return rc;
   // A failed rebuild must not leave a context that still claims to be built.
@@ -863,11 +974,13 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
 
 int mox_launch(mox_ctx* c, int32_t randSeed) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_PAR(c, mox_launch(k, randSeed));
   return renderSeeds(c, std::vector<int32_t>{randSeed});
 }
 
 int mox_render(mox_ctx* c, uint32_t spp, uint32_t seed) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_PAR(c, mox_render(k, spp, seed));
   std::vector<int32_t> seeds(spp);
   for (uint32_t i = 0; i < spp; ++i) seeds[i] = (int32_t)tea16((uint32_t)(c->launches + i), seed);
   return renderSeeds(c, seeds);
@@ -875,6 +988,20 @@ int mox_render(mox_ctx* c, uint32_t spp, uint32_t seed) {
 
 int mox_read_accum(mox_ctx* c, float* dst) {
   if (!c) return MOX_ERR_INVALID;
+  if (c->group) {
+    const float* p = nullptr;
+    int rc_ = mox_read_accum_begin(c);
+    if (!rc_) rc_ = mox_read_accum_end(c, &p);
+    if (rc_) return rc_;
+    if (!dst) return fail(c, MOX_ERR_INVALID, "null destination");
+    mox_stats st;
+    uint64_t w = 0, h = 0;
+    (void)st;
+    mox_ctx* k0 = groupChild(c->group, 0);
+    w = k0->accuW; h = k0->accuH;
+    memcpy(dst, p, (size_t)w * h * 12);
+    return MOX_OK;
+  }
   if (!dst || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
   int rc = bind(c);
   if (rc) return rc;
@@ -888,6 +1015,10 @@ int mox_read_accum(mox_ctx* c, float* dst) {
 
 int mox_map_accum(mox_ctx* c, const float** out) {
   if (!c) return MOX_ERR_INVALID;
+  if (c->group) {
+    int rc_ = mox_read_accum_begin(c);
+    return rc_ ? rc_ : mox_read_accum_end(c, out);
+  }
   if (!out || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
   int rc = bind(c);
   if (rc) return rc;
@@ -901,8 +1032,141 @@ int mox_map_accum(mox_ctx* c, const float** out) {
 
 int mox_unmap_accum(mox_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
 
+// ---- asynchronous read-back and the peer-memory tile gather (see include/mox.h)
+float* ctxGatherBuffer(mox_ctx* c, int which) {
+  if (bind(c) || ensureGather(c, true)) return nullptr;
+  if (c->gatherPeer[which]) { c->err = "gather buffer is imported"; return nullptr; }
+  cudaStreamSynchronize(c->stream);   // the zero-fill of a fresh buffer
+  return c->dGather[which];
+}
+
+int ctxBorrowGatherTarget(mox_ctx* c, int which, float* ptr) {
+  if (c->dGather[which] == ptr) return MOX_OK;
+  if (bind(c)) return MOX_ERR_CUDA;
+  if (c->dGather[which]) {
+    cudaStreamSynchronize(c->stream);
+    if (c->gatherPeer[which] == 1) cudaIpcCloseMemHandle(c->dGather[which]);
+    else if (!c->gatherPeer[which]) cudaFree(c->dGather[which]);
+  }
+  c->dGather[which] = ptr;
+  c->gatherPeer[which] = 2;   // borrowed from another context of this process: never freed here
+  c->gatherBytes = (size_t)c->accuW * c->accuH * 12;
+  return MOX_OK;
+}
+
+int mox_gather_export(mox_ctx* c, int which, void* handle_out) {
+  if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
+  if (!handle_out || which < 0 || which > 1) return fail(c, MOX_ERR_INVALID, "bad gather_export arguments");
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = ensureGather(c, true))) return rc;
+  if (c->gatherPeer[which]) return fail(c, MOX_ERR_STATE, "this rank imported its gather buffer");
+  CUCK(c, cudaStreamSynchronize(c->stream));
+  static_assert(sizeof(cudaIpcMemHandle_t) == MOX_IPC_HANDLE_BYTES, "IPC handle size");
+  CUCK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out, c->dGather[which]));
+  return MOX_OK;
+}
+
+int mox_gather_import(mox_ctx* c, int which, const void* handle) {
+  if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
+  if (!handle || which < 0 || which > 1) return fail(c, MOX_ERR_INVALID, "bad gather_import arguments");
+  if (!c->dAccu) return fail(c, MOX_ERR_STATE, "mox_gather_import before mox_set_globals");
+  int rc = bind(c);
+  if (rc) return rc;
+  if (c->dGather[which]) {
+    cudaStreamSynchronize(c->stream);
+    if (c->gatherPeer[which] == 1) cudaIpcCloseMemHandle(c->dGather[which]);
+    else if (!c->gatherPeer[which]) cudaFree(c->dGather[which]);
+    c->dGather[which] = nullptr;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void* p = nullptr;
+  CUCK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->dGather[which] = (float*)p;
+  c->gatherPeer[which] = 1;
+  c->gatherBytes = (size_t)c->accuW * c->accuH * 12;
+  return MOX_OK;
+}
+
+int mox_gather_push(mox_ctx* c, int which) {
+  if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
+  if (which < 0 || which > 1 || !c->dAccu) return fail(c, MOX_ERR_INVALID, "bad gather_push");
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = refreshOwned(c))) return rc;
+  if (!c->dGather[which] && (rc = ensureGather(c, false))) return rc;   // the root (or a single rank) pushes into its own buffer
+  launchPushOwned(c->dAccu, c->dOwned, c->nOwned, c->dGather[which], c->stream);
+  CUCK(c, cudaStreamSynchronize(c->stream));   // the pixels have landed before a barrier tells the root to read them
+  return MOX_OK;
+}
+
+int mox_read_gathered_begin(mox_ctx* c, int which) {
+  if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
+  if (which < 0 || which > 1) return fail(c, MOX_ERR_INVALID, "bad buffer index");
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = ensureGather(c, true))) return rc;
+  if (c->gatherPeer[which]) return fail(c, MOX_ERR_STATE, "only the rank that owns the gather buffer reads it");
+  // pushes of this rank are ordered by its stream, pushes of the others by the caller's barrier
+  CUCK(c, cudaEventRecord(c->evPushed, c->stream));
+  CUCK(c, cudaStreamWaitEvent(c->copyStream, c->evPushed, 0));
+  CUCK(c, cudaMemcpyAsync(c->hostGather[which], c->dGather[which], c->gatherBytes, cudaMemcpyDeviceToHost, c->copyStream));
+  CUCK(c, cudaEventRecord(c->evCopied[which], c->copyStream));
+  return MOX_OK;
+}
+
+int mox_read_gathered_end(mox_ctx* c, int which, const float** out) {
+  if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
+  if (which < 0 || which > 1 || !out || !c->hostGather[which]) return fail(c, MOX_ERR_INVALID, "bad read_gathered_end");
+  CUCK(c, cudaEventSynchronize(c->evCopied[which]));
+  *out = c->hostGather[which];
+  return MOX_OK;
+}
+
+int mox_read_accum_begin(mox_ctx* c) {
+  if (!c) return MOX_ERR_INVALID;
+  if (c->group) {
+    int rc_ = groupReadBegin(c->group);
+    if (rc_) c->err = groupError(c->group);
+    return rc_;
+  }
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = ensureGather(c, true))) return rc;
+  const int which = c->readCur;
+  if (c->gatherPeer[which]) return fail(c, MOX_ERR_STATE, "this rank's gather buffers are imported: use mox_gather_push");
+  // snapshot on the render stream (the next launch may start right away), copy on the copy stream; the snapshot
+  // must not overwrite an image the copy stream is still sending
+  CUCK(c, cudaStreamWaitEvent(c->stream, c->evCopied[which], 0));
+  CUCK(c, cudaMemcpyAsync(c->dGather[which], c->dAccu, c->gatherBytes, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = mox_read_gathered_begin(c, which))) return rc;
+  c->readPending = which;
+  c->readCur ^= 1;
+  return MOX_OK;
+}
+
+int mox_read_accum_end(mox_ctx* c, const float** out) {
+  if (!c) return MOX_ERR_INVALID;
+  if (c->group) {
+    int rc_ = groupReadEnd(c->group, out);
+    if (rc_) c->err = groupError(c->group);
+    return rc_;
+  }
+  if (c->readPending < 0) return fail(c, MOX_ERR_STATE, "mox_read_accum_end without mox_read_accum_begin");
+  int rc = mox_read_gathered_end(c, c->readPending, out);
+  c->readPending = -1;
+  return rc;
+}
+
 int mox_clear_accum(mox_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_clear_accum(k));
   int rc = bind(c);
   if (rc) return rc;
   if (c->dAccu) CUCK(c, cudaMemsetAsync(c->dAccu, 0, (size_t)c->accuW * c->accuH * 12, c->stream));
@@ -917,6 +1181,7 @@ int mox_clear_accum(mox_ctx* c) {
 
 int mox_set_accum(mox_ctx* c, const float* src, uint64_t launches) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_set_accum(k, src, launches));   // every device keeps the pixels it owns
   if (!src || !c->dAccu) return fail(c, MOX_ERR_INVALID, "no accumulation buffer");
   int rc = bind(c);
   if (rc) return rc;
@@ -928,6 +1193,7 @@ int mox_set_accum(mox_ctx* c, const float* src, uint64_t launches) {
 
 int mox_update_sphere(mox_ctx* c, uint32_t prim_id, const SphereParams* s) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_EACH(c, mox_update_sphere(k, prim_id, s));
   if (!s || prim_id >= c->prims.size() || (c->prims[prim_id].typeMat & 3u) != PT_SPHERE) return fail(c, MOX_ERR_INVALID, "not a sphere primitive");
   c->analytic[c->prims[prim_id].geom].a = make_float4(s->center.x, s->center.y, s->center.z, s->radius);
   c->built = false;
@@ -936,6 +1202,7 @@ int mox_update_sphere(mox_ctx* c, uint32_t prim_id, const SphereParams* s) {
 
 int mox_owned_pixels(mox_ctx* c, uint32_t rank, uint64_t* out_n) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile partition");
   if (!out_n || rank >= c->world || !c->haveGlobals) return fail(c, MOX_ERR_INVALID, "bad owned_pixels query");
   // closed form: no need to enumerate the pixels
   uint32_t W = c->rp.W, H = c->rp.H, T = c->tile, tx = (W + T - 1) / T, ty = (H + T - 1) / T;
@@ -949,6 +1216,7 @@ int mox_owned_pixels(mox_ctx* c, uint32_t rank, uint64_t* out_n) {
 
 int mox_pack_owned(mox_ctx* c, void* dev_dst) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
   if (!dev_dst || !c->dAccu) return fail(c, MOX_ERR_INVALID, "bad pack_owned");
   int rc = bind(c);
   if (rc) return rc;
@@ -960,6 +1228,7 @@ int mox_pack_owned(mox_ctx* c, void* dev_dst) {
 
 int mox_unpack_owned(mox_ctx* c, uint32_t rank, const void* dev_src) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_REFUSE(c, "the tile gather");
   if (!dev_src || !c->dAccu || rank >= c->world) return fail(c, MOX_ERR_INVALID, "bad unpack_owned");
   int rc = bind(c);
   if (rc) return rc;
@@ -980,6 +1249,12 @@ int mox_unpack_owned(mox_ctx* c, uint32_t rank, const void* dev_src) {
 
 int mox_get_stats(mox_ctx* c, mox_stats* s) {
   if (!c) return MOX_ERR_INVALID;
+  if (c->group) {
+    if (!s) return fail(c, MOX_ERR_INVALID, "null stats");
+    int rc_ = groupStats(c->group, s);
+    if (rc_) c->err = groupError(c->group);
+    return rc_;
+  }
   if (!s) return fail(c, MOX_ERR_INVALID, "null stats");
   memset(s, 0, sizeof *s);
   s->rays_primary = c->raysPrimary; s->rays_bounce = c->raysBounce; s->rays_shadow = c->raysShadow;
@@ -1000,6 +1275,7 @@ int mox_get_stats(mox_ctx* c, mox_stats* s) {
 
 int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* dev_hits, float* out_ms) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_FIRST(c, mox_trace_closest_device(k, dev_rays, n, dev_hits, out_ms));
   if (n && (!dev_rays || !dev_hits)) return fail(c, MOX_ERR_INVALID, "null argument");
   if (n > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "too many rays");
   if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
@@ -1037,6 +1313,7 @@ int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* d
 
 int mox_trace_closest(mox_ctx* c, const float* rays, size_t n, void* hits) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_FIRST(c, mox_trace_closest(k, rays, n, hits));
   if (n && (!rays || !hits)) return fail(c, MOX_ERR_INVALID, "null argument");
   if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
   if (!n) return MOX_OK;
@@ -1059,6 +1336,7 @@ int mox_trace_closest(mox_ctx* c, const float* rays, size_t n, void* hits) {
 
 int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_FIRST(c, mox_trace_shadow(k, rays, n, out_rgb));
   if (n && (!rays || !out_rgb)) return fail(c, MOX_ERR_INVALID, "null argument");
   if (n > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "too many rays");
   if (!c->built) return fail(c, MOX_ERR_STATE, "trace before mox_build_accel");
@@ -1096,6 +1374,7 @@ int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
 // ---- debug / test hooks (not part of the drop-in surface; declared in include/mox_debug.h)
 extern "C" int mox_debug_radix_sort(mox_ctx* c, uint32_t* keys, uint32_t* vals, size_t n) {
   if (!c) return MOX_ERR_INVALID;
+  GROUP_FIRST(c, mox_debug_radix_sort(k, keys, vals, n));
   if (n && (!keys || !vals)) return fail(c, MOX_ERR_INVALID, "null argument");
   if (!n) return MOX_OK;
   int rc = bind(c);

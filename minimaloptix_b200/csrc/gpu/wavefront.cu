@@ -17,6 +17,7 @@
 // carries throughput T and radiance R: R += T*B, T *= A.
 #include "wavefront.h"
 
+#include <atomic>
 #include <cstdlib>
 
 #include "shading.cuh"
@@ -499,6 +500,17 @@ __global__ void k_unpack_owned(float* __restrict__ accu, const uint32_t* __restr
   accu[3 * (size_t)pix + 2] = src[3 * (size_t)j + 2];
 }
 
+// Tile gather without staging: every owned pixel goes straight to its place in the full-size destination, which
+// may be peer memory (another GPU's gather buffer, mapped with P2P or CUDA IPC).  One thread per float; the owned
+// list is in tile order, so a warp writes runs of 96 contiguous floats.
+__global__ void k_push_owned(const float* __restrict__ accu, const uint32_t* __restrict__ ownedPix, uint32_t nOwned, float* __restrict__ dstFull) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nOwned * 3) return;
+  uint32_t j = (uint32_t)(i / 3), k = (uint32_t)(i - (size_t)j * 3);
+  size_t at = 3 * (size_t)ownedPix[j] + k;
+  dstFull[at] = accu[at];
+}
+
 inline unsigned grid(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
 
 }  // namespace
@@ -509,15 +521,20 @@ void launchGenerate(const LaunchCtx& c, uint32_t nSamples) {
   if (c.rp.rngMode == 0) k_generate<0><<<grid(n), TPB, 0, c.stream>>>(c, n);
   else k_generate<1><<<grid(n), TPB, 0, c.stream>>>(c, n);
 }
+// Launch geometry of the persistent kernels.  Called from several host threads (one per device of a multi-GPU
+// handle): the cached values are written once each, atomically; every device of a box is the same GPU model.
 template <class K>
-static unsigned persistentGridFor(K kernel, uint32_t count, int& blocksPerSm) {
-  static int numSms = 0;
-  if (!numSms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev); }
-  if (!blocksPerSm) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, TRAV_TPB, 0);
-    if (blocksPerSm < 1) blocksPerSm = 1;
+static unsigned persistentGridFor(K kernel, uint32_t count, std::atomic<int>& blocksPerSm) {
+  static std::atomic<int> numSms{0};
+  int sms = numSms.load(std::memory_order_relaxed);
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); numSms.store(sms, std::memory_order_relaxed); }
+  int bps = blocksPerSm.load(std::memory_order_relaxed);
+  if (!bps) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, TRAV_TPB, 0);
+    if (bps < 1) bps = 1;
+    blocksPerSm.store(bps, std::memory_order_relaxed);
   }
-  unsigned full = (unsigned)(numSms * blocksPerSm);
+  unsigned full = (unsigned)(sms * bps);
   unsigned need = (count + TRAV_TPB - 1) / TRAV_TPB;
   return need < full ? need : full;
 }
@@ -528,19 +545,21 @@ static unsigned persistentGridFor(K kernel, uint32_t count, int& blocksPerSm) {
 #define MOX_FETCH_THRESHOLD_CLOSEST 24
 #endif
 static int fetchThreshold(bool anyHit) {
-  static int t[2] = {-1, -1};
-  if (t[0] < 0) {
+  struct T { int t[2]; };
+  static const T v = [] {   // thread-safe one-time initialisation
+    T r;
     const char* e = getenv("MOX_FETCH_THRESHOLD");
-    t[0] = e ? atoi(e) : MOX_FETCH_THRESHOLD_CLOSEST;
-    t[1] = e ? atoi(e) : MOX_FETCH_THRESHOLD;
-    for (int k = 0; k < 2; ++k) t[k] = t[k] < 1 ? 1 : t[k] > 32 ? 32 : t[k];
-  }
-  return t[anyHit ? 1 : 0];
+    r.t[0] = e ? atoi(e) : MOX_FETCH_THRESHOLD_CLOSEST;
+    r.t[1] = e ? atoi(e) : MOX_FETCH_THRESHOLD;
+    for (int k = 0; k < 2; ++k) r.t[k] = r.t[k] < 1 ? 1 : r.t[k] > 32 ? 32 : r.t[k];
+    return r;
+  }();
+  return v.t[anyHit ? 1 : 0];
 }
 
 template <bool ANYHIT, bool COUNT, bool CLASSIFY>
 static void launchTraverseT(const SceneView& s, const TraceJob& job, cudaStream_t stream) {
-  static int bpsBinary = 0, bpsWide = 0;
+  static std::atomic<int> bpsBinary{0}, bpsWide{0};
   if (s.nodes8) k_traverse_wide<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse_wide<ANYHIT, COUNT, CLASSIFY>, job.count, bpsWide), TRAV_TPB, 0, stream>>>(s, job);
   else k_traverse<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse<ANYHIT, COUNT, CLASSIFY>, job.count, bpsBinary), TRAV_TPB, 0, stream>>>(s, job);
 }
@@ -621,6 +640,9 @@ void launchCopyRgb(const float4* src, float* dst, size_t n, cudaStream_t stream)
 }
 void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream) {
   if (nOwned) k_pack_owned<<<grid(nOwned), TPB, 0, stream>>>(accu, ownedPix, nOwned, dst);
+}
+void launchPushOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dstFull, cudaStream_t stream) {
+  if (nOwned) k_push_owned<<<grid((size_t)nOwned * 3), TPB, 0, stream>>>(accu, ownedPix, nOwned, dstFull);
 }
 void launchUnpackOwned(float* accu, const uint32_t* ownedPix, uint32_t nOwned, const float* src, cudaStream_t stream) {
   if (nOwned) k_unpack_owned<<<grid(nOwned), TPB, 0, stream>>>(accu, ownedPix, nOwned, src);

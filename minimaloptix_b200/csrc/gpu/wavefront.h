@@ -69,3 +69,5 @@ void launchFillOnes(float4* p, size_t n, cudaStream_t stream);
 void launchCopyRgb(const float4* src, float* dst, size_t n, cudaStream_t stream);
 void launchPackOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dst, cudaStream_t stream);
 void launchUnpackOwned(float* accu, const uint32_t* ownedPix, uint32_t nOwned, const float* src, cudaStream_t stream);
+// dst[pix] = accu[pix] for the owned pixels; dst may live on another GPU (peer stores over NVLink).
+void launchPushOwned(const float* accu, const uint32_t* ownedPix, uint32_t nOwned, float* dstFull, cudaStream_t stream);

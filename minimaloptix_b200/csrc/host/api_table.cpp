@@ -17,5 +17,8 @@ bool loadMoxApi(const char* libPath, const char* prefix, MoxApi& api, std::strin
   BIND(set_lights); BIND(clear_scene); BIND(build_accel); BIND(launch); BIND(render); BIND(read_accum);
   BIND(clear_accum); BIND(get_stats); BIND(set_accum); BIND(update_sphere);
 #undef BIND
+  api.create_multi = (int (*)(mox_ctx**, const int*, int))dlsym(lib, (std::string(prefix) + "create_multi").c_str());
+  api.read_accum_begin = (int (*)(mox_ctx*))dlsym(lib, (std::string(prefix) + "read_accum_begin").c_str());
+  api.read_accum_end = (int (*)(mox_ctx*, const float**))dlsym(lib, (std::string(prefix) + "read_accum_end").c_str());
   return ok;
 }

@@ -29,6 +29,10 @@ struct MoxApi {
   int (*get_stats)(mox_ctx*, mox_stats*) = nullptr;
   int (*set_accum)(mox_ctx*, const float*, uint64_t) = nullptr;
   int (*update_sphere)(mox_ctx*, uint32_t, const SphereParams*) = nullptr;
+  // Optional (not every backend has several devices): null when the library does not export them.
+  int (*create_multi)(mox_ctx**, const int*, int) = nullptr;
+  int (*read_accum_begin)(mox_ctx*) = nullptr;
+  int (*read_accum_end)(mox_ctx*, const float**) = nullptr;
 };
 
 // prefix is "mox_" for the product library.  Returns false and fills err on failure.

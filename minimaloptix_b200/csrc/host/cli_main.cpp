@@ -17,18 +17,20 @@
 static void usage() {
   fprintf(stderr,
           "usage: mox_cli --scene NAME [--scene-dir DIR] [--width W --height H] [--spp N] [--max-depth D]\n"
-          "               [--seed S] [--rng ref|philox] [--out PREFIX] [--snapshots] [--dump-accum] [--resume FILE.moxa] [--device K]\n"
+          "               [--seed S] [--rng ref|philox] [--out PREFIX] [--snapshots] [--dump-accum] [--resume FILE.moxa] [--device K | --gpus N]\n"
           "               [--param P] [--lib PATH]\n"
           "  NAME: spheres_lens spheres_pinhole random_spheres interior soup, or a folder under DIR\n"
           "        holding NAME.scene (coffee, cornell, ...).  Defaults are the reference's constants\n"
-          "        (1920x1080, 32 spp, depth 256; MinimalOptiX.h:82-89).\n");
+          "        (1920x1080, 32 spp, depth 256; MinimalOptiX.h:82-89); a .scene file's properties{width,height}\n"
+          "        replace 1920x1080.  --gpus N renders on devices 0..N-1 of this process (tile-split, scene\n"
+          "        replicated, tiles gathered over NVLink into device 0).\n");
 }
 
 int main(int argc, char** argv) {
   std::string scene = "spheres_lens", dir = "scenes", out = "out", lib, rng = "ref", resume;
   uint32_t W = 0, H = 0, spp = 32, depth = 256, seed = 0xC0FFEE;
   uint64_t param = 0;
-  int device = 0;
+  int device = 0, gpus = 0;
   bool snapshots = false, dumpAccum = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
@@ -46,6 +48,7 @@ int main(int argc, char** argv) {
     else if (a == "--dump-accum") dumpAccum = true;
     else if (a == "--resume") resume = val();
     else if (a == "--device") device = atoi(val());
+    else if (a == "--gpus") gpus = atoi(val());
     else if (a == "--param") param = strtoull(val(), nullptr, 0);
     else if (a == "--lib") lib = val();
     else { usage(); return 2; }
@@ -71,7 +74,12 @@ int main(int argc, char** argv) {
   if (!H) H = sc.defaultHeight;
 
   mox_ctx* ctx = nullptr;
-  if (api.create(&ctx, device)) { fprintf(stderr, "mox_create: %s\n", api.last_error(nullptr)); return 1; }
+  if (gpus > 0) {
+    if (!api.create_multi) { fprintf(stderr, "%s has no mox_create_multi\n", lib.c_str()); return 1; }
+    std::vector<int> ids(gpus);
+    for (int i = 0; i < gpus; ++i) ids[i] = i;
+    if (api.create_multi(&ctx, ids.data(), gpus)) { fprintf(stderr, "mox_create_multi: %s\n", api.last_error(nullptr)); return 1; }
+  } else if (api.create(&ctx, device)) { fprintf(stderr, "mox_create: %s\n", api.last_error(nullptr)); return 1; }
   api.set_rng_mode(ctx, rng == "philox" ? MOX_RNG_PHILOX : MOX_RNG_REF);
   if (!moxh::uploadScene(sc, api, ctx, W, H, depth, err)) { fprintf(stderr, "upload: %s\n", err.c_str()); return 1; }
   float buildMs = 0;
@@ -108,11 +116,11 @@ int main(int argc, char** argv) {
   printf("{\"scene\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"max_depth\": %u, \"seed\": %u, \"rng\": \"%s\", "
          "\"triangles\": %u, \"prims\": %u, \"bvh_build_ms\": %.3f, \"render_ms\": %.3f, \"wall_s\": %.3f, "
          "\"rays_primary\": %llu, \"rays_bounce\": %llu, \"rays_shadow\": %llu, \"mrays_per_s\": %.2f, \"mshadow_per_s\": %.2f, "
-         "\"spp_per_s\": %.3f, \"nonfinite\": %llu}\n",
+         "\"spp_per_s\": %.3f, \"nonfinite\": %llu, \"gpus\": %d}\n",
          scene.c_str(), W, H, spp, depth, seed, rng.c_str(), st.n_triangles, st.n_prims, buildMs, st.ms_render, sec,
          (unsigned long long)st.rays_primary, (unsigned long long)st.rays_bounce, (unsigned long long)st.rays_shadow,
          rays / (st.ms_render * 1e3), (double)st.rays_shadow / (st.ms_render * 1e3), spp / (st.ms_render * 1e-3),
-         (unsigned long long)st.nonfinite_samples);
+         (unsigned long long)st.nonfinite_samples, gpus > 0 ? gpus : 1);
   api.destroy(ctx);
   return 0;
 }

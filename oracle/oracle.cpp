@@ -784,6 +784,10 @@ int orc_read_accum(orc_ctx* c, float* dst) {
 }
 int orc_map_accum(orc_ctx* c, const float** out) { if (!c || !out) return MOX_ERR_INVALID; *out = c->accu.data(); return MOX_OK; }
 int orc_unmap_accum(orc_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
+int orc_device_count(const orc_ctx* c) { return c ? 1 : 0; }
+// host memory already: begin is a no-op, end hands out the accumulation buffer
+int orc_read_accum_begin(orc_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
+int orc_read_accum_end(orc_ctx* c, const float** out) { return orc_map_accum(c, out); }
 int orc_clear_accum(orc_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
   std::fill(c->accu.begin(), c->accu.end(), 0.f);

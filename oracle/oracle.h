@@ -34,6 +34,9 @@ int orc_render(orc_ctx*, uint32_t spp, uint32_t seed);
 int orc_read_accum(orc_ctx*, float* dst_rgb);
 int orc_map_accum(orc_ctx*, const float** out);
 int orc_unmap_accum(orc_ctx*);
+int orc_device_count(const orc_ctx*);
+int orc_read_accum_begin(orc_ctx*);
+int orc_read_accum_end(orc_ctx*, const float** out);
 int orc_clear_accum(orc_ctx*);
 int orc_set_accum(orc_ctx*, const float* src_rgb, uint64_t launches);
 int orc_update_sphere(orc_ctx*, uint32_t prim_id, const SphereParams*);

@@ -467,6 +467,9 @@ int ref_read_accum(ref_ctx* c, float* dst) {
 }
 int ref_map_accum(ref_ctx* c, const float** out) { if (!c || !out) return MOX_ERR_INVALID; *out = (const float*)c->accu.data(); return MOX_OK; }
 int ref_unmap_accum(ref_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
+int ref_device_count(const ref_ctx* c) { return c ? 1 : 0; }
+int ref_read_accum_begin(ref_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
+int ref_read_accum_end(ref_ctx* c, const float** out) { return ref_map_accum(c, out); }
 int ref_clear_accum(ref_ctx* c) {
   if (!c) return MOX_ERR_INVALID;
   std::fill(c->accu.begin(), c->accu.end(), float3{0, 0, 0});

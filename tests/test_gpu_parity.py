@@ -652,3 +652,103 @@ def test_error_paths(host, api_tables, gpu_backend):
                    S.LambertianParams(S.float3(1, 1, 1)))
     with pytest.raises(MoxError):
         g.set_partition(3, 2, 32)
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU handle
+def _render_image(ctx, sc, api, w, h, spp, seed):
+    sc.upload(api, ctx, w, h, 5)
+    ctx.build_accel()
+    ctx.render(spp, seed)
+    return ctx.read_accum(), ctx.stats()
+
+
+def test_multi_handle_on_one_device_equals_plain_context(host, api_tables, gpu_backend):
+    """mox_create_multi with a single device goes through the whole group machinery (forwarded scene calls, worker
+    thread, push into the gather buffer, asynchronous read-back) and must give the plain context's image bit for bit."""
+    sc = host.Scene.builtin("interior", 20000)
+    want, st0 = _render_image(gpu_backend.context(0), sc, api_tables.gpu, 200, 120, 3, 17)
+    m = gpu_backend.multi_context([0])
+    assert m.device_count() == 1
+    got, st1 = _render_image(m, sc, api_tables.gpu, 200, 120, 3, 17)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (st0["rays_bounce"], st0["rays_shadow"]) == (st1["rays_bounce"], st1["rays_shadow"])
+    from minimaloptix_b200 import MoxError
+    with pytest.raises(MoxError):
+        m.set_partition(0, 2, 32)     # the handle owns the partition
+    # raw queries go to device 0
+    rays = random_rays(5000, [0.05, 0.05, 0.05], [9.95, 3.95, 7.95], 3)
+    g = gpu_backend.context(0)
+    sc.upload(api_tables.gpu, g, 64, 64, 5); g.build_accel()
+    assert all(np.array_equal(a, b) for a, b in zip(m.trace_closest(rays), g.trace_closest(rays)))
+
+
+def test_asynchronous_readback_double_buffer(host, api_tables, gpu_backend):
+    """mox_read_accum_begin/_end: the snapshot is taken at _begin, rendering continues, two host images alternate."""
+    sc = host.Scene.builtin("spheres_lens")
+    g = gpu_backend.context(0)
+    sc.upload(api_tables.gpu, g, 160, 90, 5)
+    g.build_accel()
+    g.render(2, 5)
+    a2 = g.read_accum()
+    g.read_accum_begin()            # snapshot of the 2-spp image ...
+    g.render(2, 5)                  # ... while 2 more samples are rendered
+    img2 = g.read_accum_end().copy()
+    a4 = g.read_accum()
+    g.read_accum_begin()
+    img4 = g.read_accum_end()
+    assert np.array_equal(img2, a2) and np.array_equal(img4, a4) and not np.array_equal(a2, a4)
+    from minimaloptix_b200 import MoxError
+    with pytest.raises(MoxError):
+        g.read_accum_end()          # nothing pending
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs")
+def test_multi_handle_two_devices_bit_identical_and_cli(host, api_tables, gpu_backend, tmp_path):
+    """Two devices behind one handle (C++ threads, tiles pushed over NVLink into device 0): the image equals the
+    one-device image bit for bit; and the headless C++ driver does the same without any Python (mox_cli --gpus 2)."""
+    import json, subprocess
+    from PIL import Image
+    sc = host.Scene.builtin("interior", 60000)
+    want, st0 = _render_image(gpu_backend.context(0), sc, api_tables.gpu, 400, 240, 4, 29)
+    m = gpu_backend.multi_context([0, 1])
+    got, st1 = _render_image(m, sc, api_tables.gpu, 400, 240, 4, 29)
+    assert m.device_count() == 2
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (st0["rays_primary"], st0["rays_bounce"], st0["rays_shadow"]) == (st1["rays_primary"], st1["rays_bounce"], st1["rays_shadow"])
+    # progressive: a second render continues the seed schedule on every device
+    m.render(2, 29)
+    g = gpu_backend.context(1)     # and a plain context on the OTHER device agrees too
+    sc.upload(api_tables.gpu, g, 400, 240, 5); g.build_accel(); g.render(6, 29)
+    assert np.array_equal(m.read_accum().view(np.uint32), g.read_accum().view(np.uint32))
+    cli = os.path.join(ROOT, "minimaloptix_b200", "mox_cli")
+    outs = []
+    for extra, name in ((["--device", "0"], "one"), (["--gpus", "2"], "two")):
+        out = str(tmp_path / name)
+        r = subprocess.run([cli, "--scene", "cornell", "--scene-dir", os.path.join(ROOT, "scenes"), "--width", "256", "--height", "256",
+                            "--max-depth", "5", "--spp", "8", "--seed", "7", "--out", out] + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append((np.asarray(Image.open(out + ".png")), json.loads(r.stdout.strip().splitlines()[-1])))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[1][1]["gpus"] == 2 and outs[0][1]["rays_bounce"] == outs[1][1]["rays_bounce"]
+
+
+@pytest.mark.skipif("_n_gpus() < 2", reason="needs two GPUs")
+def test_peer_memory_gather_across_processes():
+    """One process per GPU (the bench.py / torchrun arrangement): every rank pushes its tiles into rank 0's gather
+    buffer through a CUDA IPC mapping; rank 0's frame equals the 1-rank frame bit for bit."""
+    import socket, subprocess, sys
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_mp_gpu_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, f"rank {r} failed:\n{outs[r]}"
+    assert "bit-identical: True" in outs[0] and "peer-memory" in outs[0]
