@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--tris", type=int, default=TRIS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="experiment: render only rank 0's tile set of an N-rank partition on this one GPU (what each GPU of an N-GPU run does)")
     return ap.parse_args()
 
 
@@ -175,6 +177,8 @@ def main():
     sc.upload(api, ctx, W, H, MAX_DEPTH)
     TILE = int(os.environ.get("MOX_BENCH_TILE", "32"))  # edge of the interleaved tiles (pixels)
     ctx.set_partition(rank, world, TILE)
+    if args.emulate_world > 1 and world == 1:
+        ctx.set_partition(0, args.emulate_world, TILE)
     build_ms = ctx.build_accel()
     cam = sc.cam_params(W, H)
 
@@ -198,7 +202,10 @@ def main():
     # ---- resident run: W warm-up steps, K timed steps + the gather
     for _ in range(args.warmup):
         step()
-    gather()  # warm-up of the exchange too (NCCL communicator set-up happens on the first collective)
+    gather()  # warm-up of the exchange too (communicator / peer-mapping set-up happens on the first call)
+    if rank == 0:
+        for _ in range(2):   # ... and of the read-back path: both pinned host images and gather buffers get allocated here
+            tiles.read()
     barrier()
     s0 = ctx.stats()
     sampler = ClockSampler(local)

@@ -106,6 +106,9 @@ struct mox_ctx {
   struct Slice {
     PathBuffers pb;
     cudaStream_t stream = nullptr;   // slice 0 uses the context stream
+    cudaStream_t shadowStream = nullptr;  // shadow traversal + k_apply of bounce b, overlapping extend + classify of bounce b+1
+    cudaEvent_t evShaded = nullptr, evApplied = nullptr;
+    bool applyPending = false;       // evApplied must be waited for before the next kernel that touches rad / the shadow buffers
     cudaEvent_t evReady = nullptr;   // the counters of the bounce in flight have landed in hostCnt
     uint32_t* hostCnt = nullptr;     // pinned: C_WORDS + BOUNCE_RING * C_BOUNCE_WORDS
     StageTimer timer;
@@ -141,6 +144,9 @@ struct mox_ctx {
   double msStage[ST_COUNT] = {0, 0, 0, 0, 0};
   uint64_t extendLaunches = 0, kernelLaunches = 0;
   size_t maxBatchPaths = 32u << 20;  // paths per wavefront (~280 B each with 4 lights); measured 4 Mi -> 947, 32 Mi -> 980 Mrays/s at 4K
+  bool overlapShadow = true;     // shadow rays of bounce b on a second stream, concurrent with the extend launch of bounce b+1 (MOX_OVERLAP_SHADOW=0: serial)
+  bool disneySplit = false;      // Disney NORMAL shading as two kernels sharing a per-hit record (MOX_DISNEY_SPLIT=0: one kernel)
+  bool hasDisneyNormal = false;  // some material runs the Disney NORMAL program (set by mox_build_accel)
   bool sortRays = false;         // reorder the extend queue by (origin cell, direction octant) from bounce 2 on
   float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {1, 1, 1};
 };
@@ -231,7 +237,7 @@ void freePaths(PathBuffers& pb) {
   for (auto& k : pb.kBuf) cudaFree(k);
   cudaFree(pb.sortScratch);
   for (auto& q : pb.qMat) cudaFree(q);
-  cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.shQueue); cudaFree(pb.counters); cudaFree(pb.seeds);
+  cudaFree(pb.shO); cudaFree(pb.shD); cudaFree(pb.shC); cudaFree(pb.shQueue); cudaFree(pb.counters); cudaFree(pb.seeds); cudaFree(pb.disneyRec); cudaFree(pb.qDisneyAlt);
   pb = PathBuffers();
 }
 
@@ -240,11 +246,11 @@ constexpr size_t kCounterWords = C_WORDS + BOUNCE_RING * C_BOUNCE_WORDS;
 // Bytes of wavefront state per path (see PathBuffers): rays, hit, throughput, radiance, RNG state, three queue
 // buffers, two key buffers, four material queues; per light a direction, a contribution and a queue entry; one
 // shadow origin when there are lights.
-size_t bytesPerPath(size_t nLights) { return 16 * 4 + 8 + 4 + 3 * 4 + 2 * 4 + 4 * 4 + (nLights ? 16 + nLights * 36 : 0); }
+size_t bytesPerPath(size_t nLights) { return 16 * 4 + 8 + 4 + 3 * 4 + 2 * 4 + 5 * 4 + (nLights ? 16 + nLights * 36 : 0) + 16 * MOX_DISNEY_REC_F4; }
 
 int ensurePaths(mox_ctx* c, PathBuffers& pb, cudaStream_t stream, size_t paths, size_t nLights, size_t nSeeds) {
   size_t slots = paths * nLights;
-  if (pb.capacity < paths || pb.shadowSlots < slots || !pb.counters) {
+  if (pb.capacity < paths || pb.shadowSlots < slots || !pb.counters || (c->disneySplit && c->hasDisneyNormal && !pb.disneyRec)) {
     cudaStreamSynchronize(stream);
     // grow geometrically so that a slowly growing sample count does not reallocate on every call
     if (pb.capacity && paths > pb.capacity) paths = std::max(paths, pb.capacity + pb.capacity / 2);
@@ -263,10 +269,12 @@ int ensurePaths(mox_ctx* c, PathBuffers& pb, cudaStream_t stream, size_t paths, 
       CUCK(c, cudaMalloc(&pb.sortScratch, radixSortScratchBytes(paths)));
     }
     for (auto& q : pb.qMat) CUCK(c, cudaMalloc(&q, paths * 4));
+    CUCK(c, cudaMalloc(&pb.qDisneyAlt, paths * 4));
     if (slots) {
       CUCK(c, cudaMalloc(&pb.shO, paths * 16)); CUCK(c, cudaMalloc(&pb.shD, slots * 16)); CUCK(c, cudaMalloc(&pb.shC, slots * 16));
       CUCK(c, cudaMalloc(&pb.shQueue, slots * 4));
     }
+    if (c->disneySplit && c->hasDisneyNormal) CUCK(c, cudaMalloc(&pb.disneyRec, paths * 16 * MOX_DISNEY_REC_F4));
     CUCK(c, cudaMalloc(&pb.counters, kCounterWords * 4));
     CUCK(c, cudaMemset(pb.counters, 0, kCounterWords * 4));
     pb.capacity = paths; pb.shadowSlots = slots;
@@ -357,6 +365,11 @@ int ensureSlice(mox_ctx* c, int k) {
     else CUCK(c, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
   }
   if (!sl.evReady) CUCK(c, cudaEventCreateWithFlags(&sl.evReady, cudaEventDisableTiming));
+  if (c->overlapShadow && !sl.shadowStream) {
+    CUCK(c, cudaStreamCreateWithFlags(&sl.shadowStream, cudaStreamNonBlocking));
+    CUCK(c, cudaEventCreateWithFlags(&sl.evShaded, cudaEventDisableTiming));
+    CUCK(c, cudaEventCreateWithFlags(&sl.evApplied, cudaEventDisableTiming));
+  }
   if (!sl.hostCnt) CUCK(c, cudaMallocHost(&sl.hostCnt, kCounterWords * 4));
   return MOX_OK;
 }
@@ -368,6 +381,7 @@ int sliceEnqueueExtend(mox_ctx* c, mox_ctx::Slice& sl) {
   StageTimer& tm = sl.timer;
   const uint32_t depth = sl.depth;
   lc.bc = bounceBlock(sl.pb, depth);
+  lc.pb.qMat[Q_DISNEY] = (depth & 1u) ? sl.pb.qMat[Q_DISNEY] : sl.pb.qDisneyAlt;   // k_apply of bounce depth-1 may still read the other one
   // bounce 1 traces exactly `bound` camera rays; later bounces read the number of spawned rays from the previous
   // bounce's counter block, `bound` (what was shaded) only sizes the grids
   const uint32_t* countPtr = depth == 1 ? nullptr : bounceBlock(sl.pb, depth - 1) + C_NEXT;
@@ -385,6 +399,7 @@ int sliceEnqueueExtend(mox_ctx* c, mox_ctx::Slice& sl) {
 
 int sliceFinish(mox_ctx* c, mox_ctx::Slice& sl) {
   StageTimer& tm = sl.timer;
+  if (sl.applyPending) { CUCK(c, cudaStreamWaitEvent(sl.stream, sl.evApplied, 0)); sl.applyPending = false; }
   tm.begin(ST_ACCUMULATE, sl.stream);
   launchAccumulate(sl.lc, sl.S);
   tm.end(sl.stream);
@@ -412,16 +427,28 @@ int sliceAdvance(mox_ctx* c, mox_ctx::Slice& sl) {
   uint32_t any = 0;
   for (int k = 0; k < Q_COUNT; ++k) { sl.matCount[k] = hostBounce[C_MAT0 + k]; any += sl.matCount[k]; }
   if (!any) return sliceFinish(c, sl);
+  // the shade kernels touch the radiance and rewrite the shadow-ray buffers: the previous bounce's k_apply first
+  if (sl.applyPending) { CUCK(c, cudaStreamWaitEvent(sl.stream, sl.evApplied, 0)); sl.applyPending = false; }
   tm.begin(ST_SHADE, sl.stream);
-  for (int k = 0; k < Q_COUNT; ++k) { launchShade(lc, k, sl.matCount[k], depth); if (sl.matCount[k]) c->kernelLaunches++; }
+  for (int k = 0; k < Q_COUNT; ++k) { launchShade(lc, k, sl.matCount[k], depth); if (sl.matCount[k]) c->kernelLaunches += (k == Q_DISNEY && lc.disneySplit) ? 2 : 1; }
   tm.end(sl.stream);
   if (sl.matCount[Q_DISNEY] && lc.scene.nLights) {
-    tm.begin(ST_SHADOW, sl.stream);
-    launchShadow(lc, sl.matCount[Q_DISNEY]);
-    tm.end(sl.stream);
-    tm.begin(ST_SHADE, sl.stream);
-    launchApply(lc, sl.matCount[Q_DISNEY]);
-    tm.end(sl.stream);
+    // Shadow rays and the NEE sum depend only on this bounce's shade kernels; the next extend launch does not
+    // depend on them.  On a second stream the two persistent traversal launches overlap: each one's last CTAs
+    // drain while the other's first CTAs already run.
+    cudaStream_t ss = sl.stream;
+    if (c->overlapShadow && sl.shadowStream) {
+      ss = sl.shadowStream;
+      CUCK(c, cudaEventRecord(sl.evShaded, sl.stream));
+      CUCK(c, cudaStreamWaitEvent(ss, sl.evShaded, 0));
+    }
+    tm.begin(ST_SHADOW, ss);
+    launchShadow(lc, sl.matCount[Q_DISNEY], ss);
+    tm.end(ss);
+    tm.begin(ST_SHADE, ss);
+    launchApply(lc, sl.matCount[Q_DISNEY], ss);
+    tm.end(ss);
+    if (ss != sl.stream) { CUCK(c, cudaEventRecord(sl.evApplied, ss)); sl.applyPending = true; }
     c->kernelLaunches += 2;
   }
   // the block bounce depth+1 will use was last written BOUNCE_RING bounces ago
@@ -450,14 +477,33 @@ int sliceAdvance(mox_ctx* c, mox_ctx::Slice& sl) {
   return sliceEnqueueExtend(c, sl);
 }
 
+int slicesFor(const mox_ctx* c, size_t paths) {
+  int K = c->nSlices;
+  if (paths < (size_t)K * 65536 || c->nOwned < (uint32_t)K) K = 1;   // tiny batches: the second stream buys nothing
+  return K;
+}
+
+// Streams, events, pinned counters and wavefront buffers for a batch of S samples per owned pixel.  renderSeeds
+// calls it before its timed region, so the first launch of a context does not time its own allocations.
+int prepareBatch(mox_ctx* c, uint32_t S) {
+  const size_t P = (size_t)S * c->nOwned;
+  const int K = slicesFor(c, P);
+  for (int k = 0; k < K; ++k) {
+    int rc = ensureSlice(c, k);
+    if (rc) return rc;
+    const uint32_t nPix = (uint32_t)((uint64_t)c->nOwned * (k + 1) / K) - (uint32_t)((uint64_t)c->nOwned * k / K);
+    if ((rc = ensurePaths(c, c->slices[k].pb, c->slices[k].stream, (size_t)S * nPix, c->lights.size(), S))) return rc;
+  }
+  return MOX_OK;
+}
+
 // One wavefront batch: `seeds.size()` samples of every owned pixel, rendered as nSlices interleaved sub-batches.
 int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
   const uint32_t S = (uint32_t)seeds.size();
   const size_t P = (size_t)S * c->nOwned;
   if (P == 0) return MOX_OK;
   if (P > 0xfffffff0ull) return fail(c, MOX_ERR_INVALID, "batch too large");
-  int K = c->nSlices;
-  if (P < (size_t)K * 65536 || c->nOwned < (uint32_t)K) K = 1;   // tiny batches: the second stream buys nothing
+  const int K = slicesFor(c, P);
   int rc;
   // slice k renders the owned pixels [first_k, first_k+1) — all S samples of a pixel stay in one slice, in launch
   // order, so the accumulated sums do not depend on the number of slices
@@ -465,10 +511,7 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
   for (int k = 0; k <= K; ++k) first[k] = (uint32_t)((uint64_t)c->nOwned * k / K);
   // all allocations first: a failure (MOX_ERR_OOM -> the caller retries with a smaller batch) must not leave
   // work of another slice in flight
-  for (int k = 0; k < K; ++k) {
-    if ((rc = ensureSlice(c, k))) return rc;
-    if ((rc = ensurePaths(c, c->slices[k].pb, c->slices[k].stream, (size_t)S * (first[k + 1] - first[k]), c->lights.size(), S))) return rc;
-  }
+  if ((rc = prepareBatch(c, S))) return rc;
   cudaEvent_t evStart = c->evFork;
   CUCK(c, cudaEventRecord(evStart, c->stream));
   for (int k = 0; k < K; ++k) {
@@ -486,6 +529,7 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     lc.nOwned = nPix;
     lc.accu = c->dAccu;
     lc.countTraversal = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
+    lc.disneySplit = c->disneySplit && pb.disneyRec != nullptr;
     lc.stream = sl.stream;
     lc.sceneLo = make_float3(c->sceneLo[0], c->sceneLo[1], c->sceneLo[2]);
     {
@@ -496,7 +540,7 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     lc.pb.qCur = pb.qBuf[sl.iCur]; lc.pb.qNext = pb.qBuf[sl.iNext];
     lc.pb.qKey = c->sortRays ? pb.kBuf[0] : nullptr;
     lc.bc = bounceBlock(pb, 1);
-    sl.S = S; sl.bound = (uint32_t)paths; sl.depth = 1; sl.done = false;
+    sl.S = S; sl.bound = (uint32_t)paths; sl.depth = 1; sl.done = false; sl.applyPending = false;
     CUCK(c, cudaMemsetAsync(pb.counters, 0, kCounterWords * 4, sl.stream));
     sl.timer.begin(ST_GENERATE, sl.stream);
     launchGenerate(lc, S);
@@ -561,6 +605,8 @@ int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
   if ((rc = syncTextures(c))) return rc;
   if (c->nOwned == 0) { c->launches += seeds.size(); return MOX_OK; }
   size_t perBatch = std::max<size_t>(1, batchCap(c) / c->nOwned);
+  rc = prepareBatch(c, (uint32_t)std::min(perBatch, seeds.size()));
+  if (rc && rc != MOX_ERR_OOM) return rc;   // out of memory: the loop below retries with smaller batches
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
   for (size_t i = 0; i < seeds.size();) {
     const size_t n = std::min(perBatch, seeds.size() - i);
@@ -702,6 +748,8 @@ int mox_create(mox_ctx** out, int device_id) {
   }
   if (const char* env = getenv("MOX_SORT_RAYS")) c->sortRays = atoi(env) != 0;
   if (const char* env = getenv("MOX_MAX_BATCH_PATHS")) { long long v = atoll(env); if (v > 0) c->maxBatchPaths = (size_t)v; }
+  if (const char* env = getenv("MOX_DISNEY_SPLIT")) c->disneySplit = atoi(env) != 0;
+  if (const char* env = getenv("MOX_OVERLAP_SHADOW")) c->overlapShadow = atoi(env) != 0;
   if (const char* env = getenv("MOX_SLICES")) c->nSlices = std::min(std::max(atoi(env), 1), (int)mox_ctx::kMaxSlices);
   memset(&c->rp, 0, sizeof c->rp);
   c->rp.maxDepth = 256; c->rp.eps = 0.001f; c->rp.minIntensity = 0.001f;
@@ -725,6 +773,9 @@ void mox_destroy(mox_ctx* c) {
   for (int k = 0; k < mox_ctx::kMaxSlices; ++k) {
     mox_ctx::Slice& sl = c->slices[k];
     if (sl.stream && k) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    if (sl.shadowStream) { cudaStreamSynchronize(sl.shadowStream); cudaStreamDestroy(sl.shadowStream); }
+    if (sl.evShaded) cudaEventDestroy(sl.evShaded);
+    if (sl.evApplied) cudaEventDestroy(sl.evApplied);
     freePaths(sl.pb);
     sl.timer.release();
     if (sl.evReady) cudaEventDestroy(sl.evReady);
@@ -933,9 +984,12 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   }
   if ((rc = syncLights(c))) return rc;
   if ((rc = syncTextures(c))) return rc;
-  for (auto& m : c->mats)
+  c->hasDisneyNormal = false;
+  for (auto& m : c->mats) {
     if (m.kind == MOX_MAT_DISNEY && (m.dis.albedoID < 0 || m.dis.albedoID > (int)c->textures.size()))
       return fail(c, MOX_ERR_INVALID, "DisneyParams.albedoID refers to a texture that was not added");
+    if (m.kind == MOX_MAT_DISNEY && m.dis.brdfType != GLASS) c->hasDisneyNormal = true;
+  }
   BuildInput in;
   in.arena = &c->buildArena;
   in.nPrims = (int)c->prims.size();

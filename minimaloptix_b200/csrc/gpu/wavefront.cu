@@ -387,6 +387,120 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   if (!spawned) c.pb.hit[s.path].y = __int_as_float(MOX_HIT_DEAD);
 }
 
+// The same program as two kernels.  k_shade_disney is 3 440 instructions at 80 registers (36 % occupancy, 12-15 % of
+// its stall samples instruction-cache misses): each half below holds ONE copy of disneyPdf / disneyEval.
+//   k_disney_nee     attributes, per-hit constants, the light loop (Material.cu:172-203), emission; leaves the
+//                    per-hit constants and the advanced RNG state for
+//   k_disney_sample  disneySample + indirect term (Material.cu:205-220) and the spawn.
+// RNG draws happen in the reference's order: all lights first, then the BSDF sample.
+#ifndef MOX_DISNEY_NEE_MINBLOCKS
+#define MOX_DISNEY_NEE_MINBLOCKS 6
+#endif
+template <int RM>
+__global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney_nee(LaunchCtx c, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
+  if (i >= count) return;
+  ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DISNEY][i], depth);
+  Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, true);
+  const DisneyParams dp = s.m->dis;
+  float3 N = faceforward3(a.Ns, -s.d, a.Ng);
+  float3 V = -s.d;
+  float3 baseColor = disneyBaseColor(c.scene, dp, a.u, a.v);
+  const DisneyHit dh(dp, baseColor, N);
+  {  // what the BSDF-sampling kernel needs, word-major so that neighbouring hits store neighbouring words
+    float4* rec = c.pb.disneyRec + i;
+    const size_t cap = c.pb.capacity;
+    rec[0] = make_float4(N.x, N.y, N.z, dh.metallic);
+    rec[cap] = make_float4(dh.Cdlin.x, dh.Cdlin.y, dh.Cdlin.z, dh.subsurface);
+    rec[2 * cap] = make_float4(dh.Cspec0.x, dh.Cspec0.y, dh.Cspec0.z, dh.roughness);
+    rec[3 * cap] = make_float4(dh.Csheen.x, dh.Csheen.y, dh.Csheen.z, dh.sheen);
+    rec[4 * cap] = make_float4(a.front.x, a.front.y, a.front.z, dh.clearcoat);
+    rec[5 * cap] = make_float4(dh.ax, dh.ay, dh.clearcoatAlpha, dh.specularAlpha);
+    rec[6 * cap] = make_float4(dh.diffuseRatio, dh.pdfRatio, 0.f, 0.f);
+  }
+  float3 Tprev = mk3(c.pb.thr[s.path]);
+  float3 L, H;
+  const int nL = c.scene.nLights;
+  uint32_t shadowCount = 0;
+  for (int li = 0; li < nL; ++li) {
+    const LightParams* lp = c.scene.lights + li;
+    float3 lpos = mk3(__ldg(&lp->position.x), __ldg(&lp->position.y), __ldg(&lp->position.z));
+    float3 pointOnLight, normalOnLight;
+    if (__ldg((const int*)&lp->shape) == SPHERE) {
+      pointOnLight = lpos + randInUnitSphere(s.rng) * __ldg(&lp->radius);
+      normalOnLight = normalize(pointOnLight - lpos);
+    } else {
+      float r1 = s.rng.rnd();
+      float r2 = s.rng.rnd();
+      pointOnLight = lpos + f3(lp->u) * r1 + f3(lp->v) * r2;
+      normalOnLight = normalize(f3(lp->normal));
+    }
+    L = pointOnLight - a.front;
+    float lightDst = length(L);
+    L = normalize(L);
+    size_t slot = (size_t)li * count + i;  // light-major: neighbouring lanes aim at the same light
+    float3 contrib = mk3(0.f);
+    if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
+      shadowCount++;
+      H = normalize(L + V);
+      float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
+      float objPdf = dh.pdf(L, H);
+      if (lightPdf > 0 && objPdf > 0) {
+        float3 brdf = dh.eval(L, V, H);
+        contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
+      }
+    }
+    float3 pc = Tprev * contrib;
+    bool trace = pc.x != 0.f || pc.y != 0.f || pc.z != 0.f;
+    c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
+    if (trace) {
+      c.pb.shD[slot] = make_float4(L.x, L.y, L.z, lightDst - c.rp.eps);
+      uint32_t pos = queuePush(c.bc + C_SHQ);
+      c.pb.shQueue[pos] = (uint32_t)slot;
+    }
+  }
+  if (nL) c.pb.shO[i] = make_float4(a.front.x, a.front.y, a.front.z, c.rp.eps);
+  if (shadowCount) atomicAdd(c.pb.counters + C_SHADOW, shadowCount);
+  {  // + emission
+    float3 e = f3(dp.emission);
+    if (e.x != 0.f || e.y != 0.f || e.z != 0.f) {
+      float3 r = mk3(c.pb.rad[s.path]) + Tprev * e;
+      c.pb.rad[s.path] = make_float4(r.x, r.y, r.z, 0.f);
+    }
+  }
+  c.pb.state[s.path] = s.rng.state;   // the sample kernel continues the stream where the light loop left it
+}
+
+#ifndef MOX_DISNEY_SAMPLE_MINBLOCKS
+#define MOX_DISNEY_SAMPLE_MINBLOCKS 8
+#endif
+template <int RM>
+__global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_SAMPLE_MINBLOCKS) k_disney_sample(LaunchCtx c, uint32_t count, uint32_t depth) {
+  uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t path = c.pb.qMat[Q_DISNEY][i];
+  const float4* rec = c.pb.disneyRec + i;
+  const size_t cap = c.pb.capacity;
+  const float4 r0 = rec[0], r1 = rec[cap], r2 = rec[2 * cap], r3 = rec[3 * cap], r4 = rec[4 * cap], r5 = rec[5 * cap], r6 = rec[6 * cap];
+  const DisneyHit dh(r0, r1, r2, r3, r4.w, r5, r6);
+  const float3 N = dh.N, V = -mk3(c.pb.rayD[path]);
+  RngT<RM> rng;
+  if (RM == 0) rng = makeRng<RM>(c.pb.state[path], 0u, 0u, depth);
+  else { PathCtx pc = pathCtx(c, path); rng = makeRng<RM>(c.pb.state[path], pc.pixel, (uint32_t)pc.launchSeed, depth); }
+  float3 L, H;
+  disneySample(rng, dh.metallic, dh.roughness, N, L, V, H);
+  bool spawned = false;
+  if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
+    float pdf = dh.pdf(L, H);
+    if (pdf > 0) {
+      float3 brdf = dh.eval(L, V, H);
+      spawn(c, path, mk3(r4), L, brdf / pdf, rng.forkState((int)depth + 1));
+      spawned = true;
+    }
+  }
+  if (!spawned) c.pb.hit[path].y = __int_as_float(MOX_HIT_DEAD);
+}
+
 __global__ void __launch_bounds__(TPB) k_apply(LaunchCtx c, uint32_t count) {
   uint32_t i = blockIdx.x * TPB + threadIdx.x;
   if (i >= count) return;
@@ -603,24 +717,29 @@ void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
       if (ref) k_shade_dielectric<0><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
       else k_shade_dielectric<1><<<grid(count), TPB, 0, c.stream>>>(c, count, depth);
       break;
-    case Q_DISNEY:
-      if (ref) k_shade_disney<0><<<(count + DISNEY_TPB - 1) / DISNEY_TPB, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
-      else k_shade_disney<1><<<(count + DISNEY_TPB - 1) / DISNEY_TPB, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
+    case Q_DISNEY: {
+      const unsigned g = (count + DISNEY_TPB - 1) / DISNEY_TPB;
+      if (c.disneySplit) {
+        if (ref) { k_disney_nee<0><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); k_disney_sample<0><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); }
+        else { k_disney_nee<1><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); k_disney_sample<1><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); }
+      } else if (ref) k_shade_disney<0><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
+      else k_shade_disney<1><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
       break;
+    }
   }
 }
-void launchShadow(const LaunchCtx& c, uint32_t disneyCount) {
+void launchShadow(const LaunchCtx& c, uint32_t disneyCount, cudaStream_t stream) {
   if (!disneyCount || c.scene.nLights == 0) return;
   size_t slots = (size_t)disneyCount * c.scene.nLights;
   TraceJob job;
   // dense queue of the slots that need a ray; its length lives in device memory (no host sync)
   job.rayO = c.pb.shO; job.rayD = c.pb.shD; job.queue = c.pb.shQueue; job.count = (uint32_t)slots;
   job.countPtr = c.bc + C_SHQ; job.originMod = disneyCount;
-  job.cursor = c.pb.counters + C_CURSOR; job.hits = nullptr; job.hits2 = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
-  launchTraverse(c.scene, job, true, c.countTraversal, c.stream);
+  job.cursor = c.pb.counters + C_CURSOR_SHADOW; job.hits = nullptr; job.hits2 = nullptr; job.shC = c.pb.shC; job.counters = c.pb.counters;
+  launchTraverse(c.scene, job, true, c.countTraversal, stream);
 }
-void launchApply(const LaunchCtx& c, uint32_t disneyCount) {
-  if (disneyCount && c.scene.nLights) k_apply<<<grid(disneyCount), TPB, 0, c.stream>>>(c, disneyCount);
+void launchApply(const LaunchCtx& c, uint32_t disneyCount, cudaStream_t stream) {
+  if (disneyCount && c.scene.nLights) k_apply<<<grid(disneyCount), TPB, 0, stream>>>(c, disneyCount);
 }
 void launchAccumulate(const LaunchCtx& c, uint32_t nSamples) {
   if (c.nOwned) k_accumulate<<<grid(c.nOwned), TPB, 0, c.stream>>>(c, nSamples);

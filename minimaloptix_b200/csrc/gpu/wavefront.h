@@ -17,7 +17,8 @@ enum ShadeQueue { Q_LAMBERT = 0, Q_METAL = 1, Q_DIELECTRIC = 2, Q_DISNEY = 3, Q_
 // Words 8.. are per batch.
 enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_SHQ = 5 /* shadow queue length */, C_BOUNCE_WORDS = 8,
                    C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
-                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_NODEVIS_SH_LO = 16, C_PRIMTEST_SH_LO = 18, C_WORDS = 20 };
+                   C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_CURSOR_SHADOW = 15 /* the shadow launch may overlap the next extend launch */,
+                   C_NODEVIS_SH_LO = 16, C_PRIMTEST_SH_LO = 18, C_WORDS = 20 };
 constexpr int BOUNCE_RING = 4;   // per-bounce counter blocks kept alive at once
 
 struct PathBuffers {
@@ -32,12 +33,16 @@ struct PathBuffers {
   uint32_t* qKey = nullptr;                          // keys written next to qNext (null: reordering off)
   uint32_t* sortScratch = nullptr;
   uint32_t* qMat[Q_COUNT] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t* qDisneyAlt = nullptr;   // second Disney queue: bounce b's k_apply may still read its queue while bounce b+1 is classified
   float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;  // shadow rays: origin per Disney path, (dir, tmax) and contribution per slot
   uint32_t* shQueue = nullptr;                            // slots that need a shadow ray
+  float4* disneyRec = nullptr;                            // MOX_DISNEY_REC_F4 words per Disney hit, word-major (word * capacity + hit)
   uint32_t* counters = nullptr;   // C_WORDS per-batch words (0..7 unused) followed by BOUNCE_RING blocks of C_BOUNCE_WORDS
   int32_t* seeds = nullptr;       // launch seed per sample of the batch
   size_t seedCap = 0;
 };
+
+#define MOX_DISNEY_REC_F4 7
 
 struct LaunchCtx {
   SceneView scene;
@@ -48,6 +53,7 @@ struct LaunchCtx {
   uint32_t nOwned;
   float* accu;               // device W*H*3
   bool countTraversal;
+  bool disneySplit;          // Disney NORMAL as two kernels (light sampling, then BSDF sampling) instead of one
   float3 sceneLo, sceneInvExt;  // ray-reordering key: 7-bit cell of the origin inside the scene box
   cudaStream_t stream;
 };
@@ -57,8 +63,9 @@ void launchGenerate(const LaunchCtx& c, uint32_t nSamples);
 void launchExtend(const LaunchCtx& c, const uint32_t* queue, uint32_t count, const uint32_t* countPtr, uint32_t depth);
 void launchClassify(const LaunchCtx& c, const uint32_t* queue, uint32_t count, const uint32_t* countPtr, uint32_t depth);
 void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth);
-void launchShadow(const LaunchCtx& c, uint32_t disneyCount);
-void launchApply(const LaunchCtx& c, uint32_t disneyCount);
+// The shadow traversal and k_apply may run on their own stream, overlapping the next bounce's extend launch.
+void launchShadow(const LaunchCtx& c, uint32_t disneyCount, cudaStream_t stream);
+void launchApply(const LaunchCtx& c, uint32_t disneyCount, cudaStream_t stream);
 void launchAccumulate(const LaunchCtx& c, uint32_t nSamples);
 // Persistent traversal over one batch of rays (closest hit or shadow transmittance).
 void launchTraverse(const SceneView& s, const TraceJob& job, bool anyHit, bool count, cudaStream_t stream, bool classify = false);

@@ -116,11 +116,13 @@ int main(int argc, char** argv) {
   printf("{\"scene\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"max_depth\": %u, \"seed\": %u, \"rng\": \"%s\", "
          "\"triangles\": %u, \"prims\": %u, \"bvh_build_ms\": %.3f, \"render_ms\": %.3f, \"wall_s\": %.3f, "
          "\"rays_primary\": %llu, \"rays_bounce\": %llu, \"rays_shadow\": %llu, \"mrays_per_s\": %.2f, \"mshadow_per_s\": %.2f, "
-         "\"spp_per_s\": %.3f, \"nonfinite\": %llu, \"gpus\": %d}\n",
+         "\"spp_per_s\": %.3f, \"nonfinite\": %llu, \"gpus\": %d, \"ms_extend\": %.2f, \"ms_shade\": %.2f, \"ms_shadow\": %.2f, "
+         "\"kernel_launches\": %llu}\n",
          scene.c_str(), W, H, spp, depth, seed, rng.c_str(), st.n_triangles, st.n_prims, buildMs, st.ms_render, sec,
          (unsigned long long)st.rays_primary, (unsigned long long)st.rays_bounce, (unsigned long long)st.rays_shadow,
          rays / (st.ms_render * 1e3), (double)st.rays_shadow / (st.ms_render * 1e3), spp / (st.ms_render * 1e-3),
-         (unsigned long long)st.nonfinite_samples, gpus > 0 ? gpus : 1);
+         (unsigned long long)st.nonfinite_samples, gpus > 0 ? gpus : 1, st.ms_extend, st.ms_shade, st.ms_shadow,
+         (unsigned long long)st.kernel_launches);
   api.destroy(ctx);
   return 0;
 }
