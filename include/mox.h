@@ -61,8 +61,13 @@ typedef enum mox_rng_mode { MOX_RNG_REF = 0, MOX_RNG_PHILOX = 1 } mox_rng_mode;
 /* mox_build_accel flags */
 #define MOX_ACCEL_DEFAULT 0u
 #define MOX_ACCEL_LBVH 1u        /* Karras radix tree instead of PLOC: fastest build, slower rays */
-#define MOX_ACCEL_COUNTERS 2u
-#define MOX_ACCEL_BINARY 4u      /* traverse the binary BVH, do not build the compressed 8-wide one */    /* traversal kernels count node visits / prim tests */
+#define MOX_ACCEL_COUNTERS 2u    /* traversal kernels count node visits / prim tests */
+#define MOX_ACCEL_BINARY 4u      /* traverse the binary BVH, do not build the compressed 8-wide one */
+#define MOX_ACCEL_WATERTIGHT 8u  /* watertight ray-triangle test (Woop, Benthin, Wald 2013) on the raw vertices instead of the
+                                    SDK's intersect_triangle (Geometry.cu:133): no ray slips between two triangles that share
+                                    an edge or a vertex.  t / beta / gamma then differ from the reference's in the last bits and
+                                    the winner can differ on epsilon ties; the oracle has the same switch (also: env
+                                    MOX_WATERTIGHT=1 at mox_build_accel, mox_cli --watertight) */
 
 typedef struct mox_stats {
   uint64_t rays_primary;      /* camera rays traced (closest hit)                 */

@@ -44,6 +44,7 @@ struct BuildInput {
                          // 48 -> 1213, 64 -> 1219, 100 -> 1248 Mrays/s, build 3.5 -> 3.8 ms (16 -> 32); 10 M soup: 16 -> 13.2 ms and
                          // 652..856 Mrays/s, 32 -> 15.2 ms and 628..832
   bool useWide = true;   // collapse the PLOC tree into the compressed 8-wide BVH
+  bool watertight = false;  // packed triangle records hold the raw vertices (p0, p1, p2) for the watertight test
 };
 
 // Scratch of the PLOC hierarchy builder (ploc.cu), allocated before the timed build.

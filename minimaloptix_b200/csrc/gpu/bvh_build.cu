@@ -339,7 +339,7 @@ __global__ void k_emit2(int n, const uint32_t* __restrict__ sortedIds, const flo
 
 __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const PrimDesc* __restrict__ prims,
                        const TriIdx* __restrict__ tris, const float* __restrict__ verts, const Analytic* __restrict__ analytic,
-                       const GpuMaterial* __restrict__ mats, float4* __restrict__ packed) {
+                       const GpuMaterial* __restrict__ mats, float4* __restrict__ packed, bool rawVerts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t id = sortedIds[i];
@@ -367,7 +367,8 @@ __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const Prim
     float3 p0 = mk3(verts[3 * t.v[0]], verts[3 * t.v[0] + 1], verts[3 * t.v[0] + 2]);
     float3 p1 = mk3(verts[3 * t.v[1]], verts[3 * t.v[1] + 1], verts[3 * t.v[1] + 2]);
     float3 p2 = mk3(verts[3 * t.v[2]], verts[3 * t.v[2] + 1], verts[3 * t.v[2] + 2]);
-    float3 e0 = p1 - p0, e1 = p0 - p2;
+    // watertight traversal: the vertices as they are (a shared vertex must have the same bits in every triangle)
+    float3 e0 = rawVerts ? p1 : p1 - p0, e1 = rawVerts ? p2 : p0 - p2;
     rec[0] = make_float4(p0.x, p0.y, p0.z, __uint_as_float(idbits));
     rec[1] = make_float4(e0.x, e0.y, e0.z, sc);
     rec[2] = make_float4(e1.x, e1.y, e1.z, ty);
@@ -504,7 +505,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   out.nInvalid = (int)hostSmall[6];
 
   if (nValid > 0 && (nValid <= 1 || !in.usePloc))
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed, in.watertight);
   if (nValid <= 1) {
     BvhNode2 root;
     root.c0xy = root.c1xy = root.cz = make_float4(MOX_FAR, MOX_FAR, MOX_FAR, MOX_FAR);
@@ -535,12 +536,12 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     std::string perr;
     if (!plocBuild(ploc, nValid, vin, boxLo, boxHi, in.plocRadius > 0 ? in.plocRadius : (nValid > 2000000 ? 16 : 32), out.nodes, out.sceneLo, out.sceneHi, &out.maxDepth, stream, perr)) return bail(perr);
     if (out.maxDepth <= MOX_TRAVERSAL_STACK - 2) {
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ploc.orderedIds, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed, in.watertight);
     if (wantWide) {
       uint32_t* ordered8 = nullptr;
       const uint32_t rootId = (uint32_t)(nValid + nValid - 2);  // the last node PLOC created
       if (!wideCollapse(ploc, nValid, rootId, arena, out.nodes8, &ordered8, &out.nNodes8, &out.wideLevels, stream, perr)) return bail(perr);
-      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed8);
+      k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, ordered8, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed8, in.watertight);
     }
     if (in.evStop) CKB(cudaEventRecord(in.evStop, stream));
     CKB(cudaStreamSynchronize(stream));
@@ -550,7 +551,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     return true;
     }
     // too deep for the traversal stack: fall through to the radix tree (depth <= 62)
-    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed);
+    k_pack<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, in.prims, in.tris, in.verts, in.analytic, in.mats, out.packed, in.watertight);
   }
   k_karras<<<divUp(nInner, B), B, 0, stream>>>(nValid, kin, children, range, parentInternal, parentLeaf);
   k_refit<<<divUp(nValid, B), B, 0, stream>>>(nValid, vin, boxLo, boxHi, children, parentInternal, parentLeaf, nodeLo, nodeHi, arrivals);

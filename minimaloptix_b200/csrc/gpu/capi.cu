@@ -66,6 +66,7 @@ struct mox_ctx {
   std::vector<Analytic> analytic;
   std::vector<GpuMaterial> mats;
   std::vector<LightParams> lights;
+  std::vector<float4> lightN;   // normalize(light.normal) per light, computed once with the device's operation sequence (vec.cuh)
   struct HostTexture { int w, h; std::vector<float> texels; };
   std::vector<HostTexture> textures;
   std::vector<cudaArray_t> texArrays;
@@ -74,7 +75,7 @@ struct mox_ctx {
   uint32_t nSpheres = 0, nQuads = 0;
 
   // device scene
-  DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights, dShadeRec;
+  DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights, dLightN, dShadeRec;
   bool shadeRecBuilt = false;
   DevBuf dQueryO, dQueryD, dQueryCounters;  // raw ray queries
   DevBuf dTexObjs;
@@ -100,9 +101,12 @@ struct mox_ctx {
   std::vector<DevBuf> otherOwned;  // cached owned lists of other ranks (unpack)
   std::vector<uint64_t> ownedCount; // cached |owned pixels| per rank of the current partition
 
-  // The owned pixels of a batch are rendered as `nSlices` independent sub-batches ("slices"), each with its own
+  // The owned pixels of a batch can be rendered as `nSlices` independent sub-batches ("slices"), each with its own
   // path buffers and stream: while the host reads one slice's material counts back, and while that slice's
-  // persistent traversal kernel drains its last rays, the other slice's kernels keep the SMs busy.
+  // persistent traversal kernel drains its last rays, the other slice's kernels keep the SMs busy.  Since the
+  // shadow rays of a bounce run on their own stream (overlapShadow) a single slice already has two traversal
+  // launches in flight, and one slice measures as fast at full frame (1347 vs 1350 Mrays/s), faster on an eighth
+  // of the frame (14.99 vs 15.16 ms per step) and end to end (1340 vs 1262): the default is 1 (MOX_SLICES=2..4).
   struct Slice {
     PathBuffers pb;
     cudaStream_t stream = nullptr;   // slice 0 uses the context stream
@@ -120,7 +124,7 @@ struct mox_ctx {
   };
   static constexpr int kMaxSlices = 4;
   Slice slices[kMaxSlices];
-  int nSlices = 2;
+  int nSlices = 1;
   float* pinned = nullptr;
   size_t pinnedBytes = 0;
 
@@ -304,9 +308,11 @@ SceneView sceneView(const mox_ctx* c) {
   s.tris = (const TriIdx*)c->dTris.p;
   s.shadeRec = c->shadeRecBuilt ? (const float4*)c->dShadeRec.p : nullptr;
   s.lights = (const LightParams*)c->dLights.p;
+  s.lightN = (const float4*)c->dLightN.p;
   s.textures = (const cudaTextureObject_t*)c->dTexObjs.p;
   s.nLights = (int)c->lights.size();
   s.nPrims = (int)c->prims.size();
+  s.watertight = (c->accelFlags & MOX_ACCEL_WATERTIGHT) ? 1 : 0;
   return s;
 }
 
@@ -352,6 +358,14 @@ int syncLights(mox_ctx* c) {
   if (!c->lightsDirty) return MOX_OK;
   int rc = upload(c, c->dLights, c->lights);
   if (rc) return rc;
+  // normalize(lp->normal) is the same for every hit (Material.cu:183): IEEE multiply / add / sqrt / divide in the
+  // order of vec.cuh's normalize give the same bits on the host as in the shade kernel
+  c->lightN.resize(c->lights.size());
+  for (size_t i = 0; i < c->lights.size(); ++i) {
+    const float3 n = normalize(mk3(c->lights[i].normal.x, c->lights[i].normal.y, c->lights[i].normal.z));
+    c->lightN[i] = make_float4(n.x, n.y, n.z, 0.f);
+  }
+  if ((rc = upload(c, c->dLightN, c->lightN))) return rc;
   c->lightsDirty = false;
   return MOX_OK;
 }
@@ -763,7 +777,7 @@ void mox_destroy(mox_ctx* c) {
   if (c->group) { groupDestroy(c->group); delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dShadeRec, &c->dQueryO,
+  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dLightN, &c->dShadeRec, &c->dQueryO,
                    &c->dQueryD, &c->dQueryCounters}) b->release();
   for (auto& b : c->otherOwned) b.release();
   freeTextures(c);
@@ -1005,6 +1019,8 @@ int mox_build_accel(mox_ctx* c, uint32_t flags, float* out_ms) {
   c->useWide = (flags & MOX_ACCEL_BINARY) == 0;
   if (const char* env = getenv("MOX_FORCE_BINARY")) { if (atoi(env)) c->useWide = false; }
   in.useWide = c->useWide;
+  if (const char* env = getenv("MOX_WATERTIGHT")) { if (atoi(env)) flags |= MOX_ACCEL_WATERTIGHT; }
+  in.watertight = (flags & MOX_ACCEL_WATERTIGHT) != 0;
   BuildOutput out;
   out.nodes = c->dNodes; out.packed = c->dPacked; out.nodesCap = c->nodesCap; out.packedCap = c->packedCap;
   out.nodes8 = c->dNodes8; out.packed8 = c->dPacked8; out.nodes8Cap = c->nodes8Cap; out.packed8Cap = c->packed8Cap;

@@ -68,7 +68,7 @@ static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
 #endif
 
 // Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.
-//   triangle: (p0, idbits) (e0 = p1 - p0, -) (e1 = p0 - p2, -)
+//   triangle: (p0, idbits) (e0 = p1 - p0, -) (e1 = p0 - p2, -); with MOX_ACCEL_WATERTIGHT the raw vertices (p0) (p1) (p2)
 //   analytic: (index into Analytic[] as int bits, -, -, idbits)
 // idbits = prim id | type << 30.
 #define MOX_PACKED_F4 3
@@ -112,9 +112,11 @@ struct SceneView {
   const TriIdx* tris;
   const float4* shadeRec;   // MOX_SHADE_REC_F4 float4 per triangle: what a hit needs for shading, pre-gathered (null: gather through tris)
   const LightParams* lights;
+  const float4* lightN;     // normalize(lights[i].normal), precomputed at upload
   const cudaTextureObject_t* textures;  // id - 1 -> float4 texture, bilinear, REPEAT, normalized coords
   int nLights;
   int nPrims;
+  int watertight;           // packed / packed8 triangle records hold raw vertices; the traversal runs the watertight test
 };
 
 struct RenderParams {

@@ -138,11 +138,38 @@ struct DisneyHit {
     pdfRatio = 1.0f / (1.0f + mp.clearcoat);
   }
 
-  // disney.h:32-46
-  MOX_D float pdf(const float3& L, const float3& H) const {
-    float specularRatio = 1.f - diffuseRatio;
+  // Terms of disneyPdf / disneyEval that depend on the view direction only (the same V for every light sample and
+  // for the sampled direction of a hit), and products of per-hit constants that the reference expressions
+  // evaluate first.  Same operations on the same operands in the same order: bit-identical results.
+  float3 V;
+  float NdotV, FV, GsV, GrV;
+  float specularRatio, ccA2m1, ccPiLog, piAxAy, quarterClearcoat, oneMinusMetallic;
+  MOX_D void setView(const float3& v) {
+    V = v;
+    NdotV = dot(N, V);
+    FV = schlickFresnel(NdotV);
+    GsV = smithGGgxAniso(NdotV, dot(V, X), dot(V, Y), ax, ay);
+    GrV = smithGGgx(NdotV, 0.25f);
+    specularRatio = 1.f - diffuseRatio;
+    float a2 = clearcoatAlpha * clearcoatAlpha;
+    ccA2m1 = a2 - 1.0f;
+    ccPiLog = MOX_PI_F * logf(a2);
+    piAxAy = MOX_PI_F * ax * ay;
+    quarterClearcoat = 0.25f * clearcoat;
+    oneMinusMetallic = 1.0f - metallic;
+  }
+  // GTR1(c, clearcoatAlpha); even in c (each rounding is sign-symmetric), so pdf (|N.H|) and eval (N.H) share it
+  MOX_D float gtr1Clearcoat(float c) const {
+    if (clearcoatAlpha >= 1.f) return 1.f / MOX_PI_F;
+    float t = 1.f + ccA2m1 * c * c;
+    return ccA2m1 / (ccPiLog * t);
+  }
+
+  // disney.h:32-46; `dr` = GTR1(|N.H|, clearcoatAlpha) for eval()
+  MOX_D float pdf(const float3& L, const float3& H, float& dr) const {
     float cosTheta = fabsf(dot(N, H));
-    float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha) * cosTheta;
+    dr = gtr1Clearcoat(cosTheta);
+    float pdfGTR1 = dr * cosTheta;
     float pdfGTR2 = GTR2(cosTheta, specularAlpha) * cosTheta;
     float pdfH = lerpf(pdfGTR1, pdfGTR2, pdfRatio);
     float pdfL = pdfH / (4.0f * fabsf(dot(L, H)));
@@ -151,24 +178,23 @@ struct DisneyHit {
   }
 
   // disney.h:48-91
-  MOX_D float3 eval(const float3& L, const float3& V, const float3& H) const {
-    float NdotL = dot(N, L), NdotV = dot(N, V), NdotH = dot(N, H), LdotH = dot(L, H);
-    float FL = schlickFresnel(NdotL), FV = schlickFresnel(NdotV);
+  MOX_D float3 eval(const float3& L, const float3& H, float Dr) const {
+    float NdotL = dot(N, L), NdotH = dot(N, H), LdotH = dot(L, H);
+    float FL = schlickFresnel(NdotL);
     float Fd90 = 0.5f + 2.f * LdotH * LdotH * roughness;
     float Fd = lerpf(1.f, Fd90, FL) * lerpf(1.f, Fd90, FV);
     float Fss90 = LdotH * LdotH * roughness;
     float Fss = lerpf(1.0f, Fss90, FL) * lerpf(1.0f, Fss90, FV);
     float ss = 1.25f * (Fss * (1.f / (NdotL + NdotV) - 0.5f) + 0.5f);
-    float Ds = GTR2Aniso(NdotH, dot(H, X), dot(H, Y), ax, ay);
+    float Ds = 1 / (piAxAy * sqr(sqr(dot(H, X) / ax) + sqr(dot(H, Y) / ay) + NdotH * NdotH));
     float FH = schlickFresnel(LdotH);
     float3 Fs = lerp3(Cspec0, mk3(1.f), FH);
-    float Gs = smithGGgxAniso(NdotL, dot(L, X), dot(L, Y), ax, ay) * smithGGgxAniso(NdotV, dot(V, X), dot(V, Y), ax, ay);
+    float Gs = smithGGgxAniso(NdotL, dot(L, X), dot(L, Y), ax, ay) * GsV;
     float3 Fsheen = FH * sheen * Csheen;
-    float Dr = GTR1(NdotH, clearcoatAlpha);
     float Fr = lerpf(0.04f, 1.f, FH);
-    float Gr = smithGGgx(NdotL, 0.25f) * smithGGgx(NdotV, 0.25f);
-    return ((1.0f / MOX_PI_F) * lerpf(Fd, ss, subsurface) * Cdlin + Fsheen) * (1.0f - metallic) + Gs * Fs * Ds +
-           mk3(0.25f * clearcoat * Gr * Fr * Dr);
+    float Gr = smithGGgx(NdotL, 0.25f) * GrV;
+    return ((1.0f / MOX_PI_F) * lerpf(Fd, ss, subsurface) * Cdlin + Fsheen) * oneMinusMetallic + Gs * Fs * Ds +
+           mk3(quarterClearcoat * Gr * Fr * Dr);
   }
 };
 

@@ -25,6 +25,51 @@ MOX_D bool triTest(const float3& o, const float3& d, float tmin, const float3& p
   return (t > tmin) & (beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1);
 }
 
+// ---- watertight ray-triangle test (Woop, Benthin, Wald 2013), opt-in with MOX_ACCEL_WATERTIGHT.
+// The SDK test above works on edges rounded from the vertices and divides by a rounded n.d: a ray aimed at an edge
+// or a vertex shared by two triangles can miss both.  This one shears and scales the three vertices — the raw
+// coordinates, identical bits for every triangle sharing them — into ray space, where each scaled edge function
+// U, V, W is evaluated from the same two sheared vertices whichever triangle asks, so two triangles sharing an
+// edge can never both reject a ray crossing it; exact zeros are re-evaluated in double (products of floats are exact
+// there, so the sign is).  No backface culling, like the SDK test.  beta / gamma weigh p1 / p2 as above.
+// oracle/oracle.cpp::watertightTriangle is the same operation sequence (no FMA on either side).
+struct WtRay { int kx, ky, kz; float Sx, Sy, Sz; };
+MOX_D float pick3(const float3& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+MOX_D WtRay wtPrep(const float3& d) {
+  WtRay w;
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  w.kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  w.kx = w.kz == 2 ? 0 : w.kz + 1;
+  w.ky = w.kx == 2 ? 0 : w.kx + 1;
+  const float dz = pick3(d, w.kz);
+  if (dz < 0.f) { const int t = w.kx; w.kx = w.ky; w.ky = t; }
+  w.Sx = pick3(d, w.kx) / dz;
+  w.Sy = pick3(d, w.ky) / dz;
+  w.Sz = 1.0f / dz;
+  return w;
+}
+MOX_D bool triTestWt(const WtRay& w, const float3& o, float tmin, const float3& p0, const float3& p1, const float3& p2,
+                     float& t, float& beta, float& gamma) {
+  const float3 A = p0 - o, B = p1 - o, C = p2 - o;
+  const float Akz = pick3(A, w.kz), Bkz = pick3(B, w.kz), Ckz = pick3(C, w.kz);
+  const float Ax = pick3(A, w.kx) - w.Sx * Akz, Ay = pick3(A, w.ky) - w.Sy * Akz;
+  const float Bx = pick3(B, w.kx) - w.Sx * Bkz, By = pick3(B, w.ky) - w.Sy * Bkz;
+  const float Cx = pick3(C, w.kx) - w.Sx * Ckz, Cy = pick3(C, w.ky) - w.Sy * Ckz;
+  float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+  if (U == 0.f || V == 0.f || W == 0.f) {
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
+  const float det = U + V + W;
+  if (det == 0.f) return false;
+  const float T = U * (w.Sz * Akz) + V * (w.Sz * Bkz) + W * (w.Sz * Ckz);
+  const float rcp = 1.0f / det;
+  t = T * rcp; beta = V * rcp; gamma = W * rcp;
+  return t > tmin;
+}
+
 // First root in (tmin, bound) — near root, else far root (Geometry.cu:18-55).  `incl`: also accept t == bound.
 MOX_D bool sphereTest(const float4& cr, const float3& o, const float3& d, float tmin, float bound, bool incl, float& t) {
   float3 oc = o - mk3(cr);
@@ -101,7 +146,7 @@ MOX_D float boxEntry(const RayPre& r, float lox, float hix, float loy, float hiy
 //   * closest hit obeys the (t, id) lexicographic rule; any hit: Disney prims only, NORMAL
 //     blocks, GLASS tints (Material.cu:225-232);
 //   * per-lane traversal stack in local memory (far children only).
-template <bool ANYHIT, bool COUNT, bool CLASSIFY = false>
+template <bool ANYHIT, bool COUNT, bool CLASSIFY = false, bool WT = false>
 __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const TraceJob& job) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -120,6 +165,8 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
   uint32_t bCls = 0;
   float3 atten = mk3(1.f);
   uint32_t nv = 0, np = 0;
+  WtRay wr;
+  wr.kx = wr.ky = wr.kz = 0; wr.Sx = wr.Sy = wr.Sz = 0.f;
 
 #define MOX_SET_CUR(c)                                             \
   do {                                                             \
@@ -147,6 +194,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
             float4 ro = MOX_LD_STREAM(job.rayO + oId), rd = MOX_LD_STREAM(job.rayD + rayId);
             if (!(ANYHIT && rd.w < 0.f)) {
               r = prepRay(mk3(ro), mk3(rd), ro.w);
+              if (WT) wr = wtPrep(r.d);
               tBest = rd.w; bPrim = -1; bBeta = 0.f; bGamma = 0.f;
               atten = mk3(1.f);
               sp = 0; cur = 0;  // root
@@ -202,7 +250,8 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
           bool hit;
           if (type == PT_TRI) {
             float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-            hit = triTest(r.o, r.d, r.tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+            hit = (WT ? triTestWt(wr, r.o, r.tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) : triTest(r.o, r.d, r.tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga)) &&
+                  (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
           } else {
             const Analytic* an = s.analytic + __float_as_int(r0.x);
             if (type == PT_SPHERE) {

@@ -43,7 +43,8 @@ MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xf
 // CLASSIFY (closest hit of the render path): the hit record is (t, primitive id | shade class << 28) — the class
 // comes from the winning primitive's packed record — and beta / gamma are not carried (two registers less per
 // lane); the shade kernels recompute them from the same operands.  The raw query keeps the four-word record.
-template <bool ANYHIT, bool COUNT, bool CLASSIFY = false>
+// WT: the packed triangle records hold the raw vertices and the watertight test runs (MOX_ACCEL_WATERTIGHT).
+template <bool ANYHIT, bool COUNT, bool CLASSIFY = false, bool WT = false>
 __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const TraceJob& job) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -65,6 +66,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   uint32_t bCls = 0;
   float3 atten = mk3(1.f);
   uint32_t nv = 0, np = 0;
+  WtRay wr;
+  wr.kx = wr.ky = wr.kz = 0; wr.Sx = wr.Sy = wr.Sz = 0.f;
 
   while (true) {
     // ---------------- refill idle lanes
@@ -84,6 +87,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
             if (!(ANYHIT && rd.w < 0.f)) {
               RayPre r = prepRay(mk3(ro), mk3(rd), ro.w);
               o = r.o; d = r.d; idir = r.idir; tmin = r.tmin;
+              if (WT) wr = wtPrep(d);
               octinv = 7u ^ ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
               tBest = rd.w; bPrim = -1;
               if (!CLASSIFY) { bBeta = 0.f; bGamma = 0.f; }
@@ -200,7 +204,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           float t = 0.f, be = 0.f, ga = 0.f;
           bool hit;
           if (type == PT_TRI) {
-            hit = triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) && (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
+            hit = (WT ? triTestWt(wr, o, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga) : triTest(o, d, tmin, mk3(r0), mk3(r1), mk3(r2), t, be, ga)) &&
+                  (t < tBest || (!ANYHIT && t == tBest && id < bPrim));
           } else if (type == PT_SPHERE) {
             hit = sphereTest(make_float4(r1.x, r1.y, r1.z, r2.x), o, d, tmin, tBest, !ANYHIT && id < bPrim, t);
           } else {

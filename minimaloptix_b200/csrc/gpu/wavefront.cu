@@ -90,6 +90,16 @@ template <bool ANYHIT, bool COUNT, bool CLASSIFY>
 __global__ void __launch_bounds__(TRAV_TPB, MOX_TRAV_MINBLOCKS) k_traverse(SceneView s, TraceJob job) {
   traverseWarpPersistent<ANYHIT, COUNT, CLASSIFY>(s, job);
 }
+// Watertight variants (MOX_ACCEL_WATERTIGHT): six more per-ray values (shear axes and scales), so one CTA less per SM
+// than the default kernels instead of spills.
+template <bool ANYHIT, bool COUNT, bool CLASSIFY>
+__global__ void __launch_bounds__(TRAV_TPB, 8) k_traverse_wt(SceneView s, TraceJob job) {
+  traverseWarpPersistent<ANYHIT, COUNT, CLASSIFY, true>(s, job);
+}
+template <bool ANYHIT, bool COUNT, bool CLASSIFY>
+__global__ void __launch_bounds__(TRAV_TPB, 8) k_traverse_wide_wt(SceneView s, TraceJob job) {
+  traverseWidePersistent<ANYHIT, COUNT, CLASSIFY, true>(s, job);
+}
 
 #ifndef MOX_WIDE_MINBLOCKS
 #define MOX_WIDE_MINBLOCKS 9   // 56 registers, no spills: measured 8 -> 1229, 9 -> 1258, 10 -> 1240 Mrays/s (before the weighted vote: 1064 / 1090 / 1069)
@@ -130,10 +140,11 @@ __device__ __forceinline__ float3 ld3(const float* p, int i) { return mk3(__ldg(
 
 // beta / gamma of a triangle hit are not stored by the traversal kernel: they are recomputed here with the
 // operation sequence of the primitive test (triTest) on the same operands — bit-identical values.
-__device__ __forceinline__ void triBarycentrics(const float3& o, const float3& d, const float3& p0, const float3& p1, const float3& p2,
-                                                float& beta, float& gamma) {
+__device__ __forceinline__ void triBarycentrics(bool watertight, const float3& o, const float3& d, const float3& p0, const float3& p1,
+                                                const float3& p2, float& beta, float& gamma) {
   float t;
-  triTest(o, d, 0.f, p0, p1 - p0, p0 - p2, t, beta, gamma);
+  if (watertight) triTestWt(wtPrep(d), o, 0.f, p0, p1, p2, t, beta, gamma);
+  else triTest(o, d, 0.f, p0, p1 - p0, p0 - p2, t, beta, gamma);
 }
 
 __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc& pd, const float3& o, const float3& d,
@@ -164,7 +175,7 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
       const uint32_t flags = __float_as_uint(r0.w);
       if (flags) {
         const float4 r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
-        triBarycentrics(o, d, p0, p1, p2, beta, gamma);
+        triBarycentrics(s.watertight != 0, o, d, p0, p1, p2, beta, gamma);
         if (flags & 1u) a.Ns = normalize(mk3(r4) * beta + mk3(r5) * gamma + mk3(r3) * (1.f - beta - gamma));
         if (flags & 2u) {
           float w = 1.0f - beta - gamma;
@@ -184,7 +195,7 @@ __device__ __forceinline__ Attr hitAttributes(const SceneView& s, const PrimDesc
     a.front = a.back = a.hitPoint;
     if (needShading) {
       int n0 = __ldg(&ti->n[0]);
-      if (n0 >= 0 || __ldg(&ti->t[0]) >= 0) triBarycentrics(o, d, p0, p1, p2, beta, gamma);
+      if (n0 >= 0 || __ldg(&ti->t[0]) >= 0) triBarycentrics(s.watertight != 0, o, d, p0, p1, p2, beta, gamma);
       if (n0 >= 0) {
         int n1 = __ldg(&ti->n[1]), n2 = __ldg(&ti->n[2]);
         a.Ns = normalize(ld3(s.normals, n1) * beta + ld3(s.normals, n2) * gamma + ld3(s.normals, n0) * (1.f - beta - gamma));
@@ -321,7 +332,8 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
   float3 baseColor = disneyBaseColor(c.scene, dp, a.u, a.v);
-  const DisneyHit dh(dp, baseColor, N);
+  DisneyHit dh(dp, baseColor, N);
+  dh.setView(V);
   float3 Tprev = mk3(c.pb.thr[s.path]);
   float3 L, H;
   const int nL = c.scene.nLights;
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
       float r1 = s.rng.rnd();
       float r2 = s.rng.rnd();
       pointOnLight = lpos + f3(lp->u) * r1 + f3(lp->v) * r2;
-      normalOnLight = normalize(f3(lp->normal));
+      normalOnLight = mk3(__ldg(c.scene.lightN + li));
     }
     L = pointOnLight - a.front;
     float lightDst = length(L);
@@ -348,9 +360,10 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
       shadowCount++;
       H = normalize(L + V);
       float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
-      float objPdf = dh.pdf(L, H);
+      float dr;
+      float objPdf = dh.pdf(L, H, dr);
       if (lightPdf > 0 && objPdf > 0) {
-        float3 brdf = dh.eval(L, V, H);
+        float3 brdf = dh.eval(L, H, dr);
         contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
       }
     }
@@ -376,9 +389,10 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   disneySample(s.rng, dp, N, L, V, H);
   bool spawned = false;
   if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
-    float pdf = dh.pdf(L, H);
+    float dr;
+    float pdf = dh.pdf(L, H, dr);
     if (pdf > 0) {
-      float3 brdf = dh.eval(L, V, H);
+      float3 brdf = dh.eval(L, H, dr);
       spawn(c, s.path, a.front, L, brdf / pdf, s.rng.forkState((int)depth + 1));
       spawned = true;
     }
@@ -406,7 +420,8 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
   float3 baseColor = disneyBaseColor(c.scene, dp, a.u, a.v);
-  const DisneyHit dh(dp, baseColor, N);
+  DisneyHit dh(dp, baseColor, N);
+  dh.setView(V);
   {  // what the BSDF-sampling kernel needs, word-major so that neighbouring hits store neighbouring words
     float4* rec = c.pb.disneyRec + i;
     const size_t cap = c.pb.capacity;
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
       float r1 = s.rng.rnd();
       float r2 = s.rng.rnd();
       pointOnLight = lpos + f3(lp->u) * r1 + f3(lp->v) * r2;
-      normalOnLight = normalize(f3(lp->normal));
+      normalOnLight = mk3(__ldg(c.scene.lightN + li));
     }
     L = pointOnLight - a.front;
     float lightDst = length(L);
@@ -444,9 +459,10 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
       shadowCount++;
       H = normalize(L + V);
       float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
-      float objPdf = dh.pdf(L, H);
+      float dr;
+      float objPdf = dh.pdf(L, H, dr);
       if (lightPdf > 0 && objPdf > 0) {
-        float3 brdf = dh.eval(L, V, H);
+        float3 brdf = dh.eval(L, H, dr);
         contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
       }
     }
@@ -482,8 +498,9 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_SAMPLE_MINBLOCKS) k_dis
   const float4* rec = c.pb.disneyRec + i;
   const size_t cap = c.pb.capacity;
   const float4 r0 = rec[0], r1 = rec[cap], r2 = rec[2 * cap], r3 = rec[3 * cap], r4 = rec[4 * cap], r5 = rec[5 * cap], r6 = rec[6 * cap];
-  const DisneyHit dh(r0, r1, r2, r3, r4.w, r5, r6);
+  DisneyHit dh(r0, r1, r2, r3, r4.w, r5, r6);
   const float3 N = dh.N, V = -mk3(c.pb.rayD[path]);
+  dh.setView(V);
   RngT<RM> rng;
   if (RM == 0) rng = makeRng<RM>(c.pb.state[path], 0u, 0u, depth);
   else { PathCtx pc = pathCtx(c, path); rng = makeRng<RM>(c.pb.state[path], pc.pixel, (uint32_t)pc.launchSeed, depth); }
@@ -491,9 +508,10 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_SAMPLE_MINBLOCKS) k_dis
   disneySample(rng, dh.metallic, dh.roughness, N, L, V, H);
   bool spawned = false;
   if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
-    float pdf = dh.pdf(L, H);
+    float dr;
+    float pdf = dh.pdf(L, H, dr);
     if (pdf > 0) {
-      float3 brdf = dh.eval(L, V, H);
+      float3 brdf = dh.eval(L, H, dr);
       spawn(c, path, mk3(r4), L, brdf / pdf, rng.forkState((int)depth + 1));
       spawned = true;
     }
@@ -673,8 +691,11 @@ static int fetchThreshold(bool anyHit) {
 
 template <bool ANYHIT, bool COUNT, bool CLASSIFY>
 static void launchTraverseT(const SceneView& s, const TraceJob& job, cudaStream_t stream) {
-  static std::atomic<int> bpsBinary{0}, bpsWide{0};
-  if (s.nodes8) k_traverse_wide<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse_wide<ANYHIT, COUNT, CLASSIFY>, job.count, bpsWide), TRAV_TPB, 0, stream>>>(s, job);
+  static std::atomic<int> bpsBinary{0}, bpsWide{0}, bpsBinaryWt{0}, bpsWideWt{0};
+  if (s.watertight) {
+    if (s.nodes8) k_traverse_wide_wt<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse_wide_wt<ANYHIT, COUNT, CLASSIFY>, job.count, bpsWideWt), TRAV_TPB, 0, stream>>>(s, job);
+    else k_traverse_wt<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse_wt<ANYHIT, COUNT, CLASSIFY>, job.count, bpsBinaryWt), TRAV_TPB, 0, stream>>>(s, job);
+  } else if (s.nodes8) k_traverse_wide<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse_wide<ANYHIT, COUNT, CLASSIFY>, job.count, bpsWide), TRAV_TPB, 0, stream>>>(s, job);
   else k_traverse<ANYHIT, COUNT, CLASSIFY><<<persistentGridFor(k_traverse<ANYHIT, COUNT, CLASSIFY>, job.count, bpsBinary), TRAV_TPB, 0, stream>>>(s, job);
 }
 

@@ -18,12 +18,12 @@ static void usage() {
   fprintf(stderr,
           "usage: mox_cli --scene NAME [--scene-dir DIR] [--width W --height H] [--spp N] [--max-depth D]\n"
           "               [--seed S] [--rng ref|philox] [--out PREFIX] [--snapshots] [--dump-accum] [--resume FILE.moxa] [--device K | --gpus N]\n"
-          "               [--param P] [--lib PATH]\n"
+          "               [--param P] [--lib PATH] [--watertight]\n"
           "  NAME: spheres_lens spheres_pinhole random_spheres interior soup, or a folder under DIR\n"
           "        holding NAME.scene (coffee, cornell, ...).  Defaults are the reference's constants\n"
           "        (1920x1080, 32 spp, depth 256; MinimalOptiX.h:82-89); a .scene file's properties{width,height}\n"
           "        replace 1920x1080.  --gpus N renders on devices 0..N-1 of this process (tile-split, scene\n"
-          "        replicated, tiles gathered over NVLink into device 0).\n");
+          "        replicated, tiles gathered over NVLink into device 0).  --watertight: MOX_ACCEL_WATERTIGHT (include/mox.h).\n");
 }
 
 int main(int argc, char** argv) {
@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
   uint32_t W = 0, H = 0, spp = 32, depth = 256, seed = 0xC0FFEE;
   uint64_t param = 0;
   int device = 0, gpus = 0;
-  bool snapshots = false, dumpAccum = false;
+  bool snapshots = false, dumpAccum = false, watertight = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto val = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
@@ -46,6 +46,7 @@ int main(int argc, char** argv) {
     else if (a == "--out") out = val();
     else if (a == "--snapshots") snapshots = true;
     else if (a == "--dump-accum") dumpAccum = true;
+    else if (a == "--watertight") watertight = true;
     else if (a == "--resume") resume = val();
     else if (a == "--device") device = atoi(val());
     else if (a == "--gpus") gpus = atoi(val());
@@ -83,7 +84,7 @@ int main(int argc, char** argv) {
   api.set_rng_mode(ctx, rng == "philox" ? MOX_RNG_PHILOX : MOX_RNG_REF);
   if (!moxh::uploadScene(sc, api, ctx, W, H, depth, err)) { fprintf(stderr, "upload: %s\n", err.c_str()); return 1; }
   float buildMs = 0;
-  if (api.build_accel(ctx, MOX_ACCEL_DEFAULT, &buildMs)) { fprintf(stderr, "build_accel: %s\n", api.last_error(ctx)); return 1; }
+  if (api.build_accel(ctx, watertight ? MOX_ACCEL_WATERTIGHT : MOX_ACCEL_DEFAULT, &buildMs)) { fprintf(stderr, "build_accel: %s\n", api.last_error(ctx)); return 1; }
 
   std::vector<float> accum((size_t)W * H * 3);
   std::vector<uint8_t> rgb((size_t)W * H * 3);

@@ -90,6 +90,7 @@ struct orc_ctx {
   int nThreads = 0;
   bool brute = false;
   bool built = false;
+  bool watertight = false;   // MOX_ACCEL_WATERTIGHT: the twin of the GPU's opt-in watertight triangle test
   int quadLightDrawOrder = 0;
 
   std::vector<Prim> prims;
@@ -194,10 +195,58 @@ bool hitQuad(const QuadParams& q, const Ray& ray, float tmaxCur, HitAttr& h) {  
   return false;
 }
 
+// Watertight ray-triangle test (Woop, Benthin, Wald 2013) — not part of the reference (its mesh program calls the
+// SDK's intersect_triangle); the twin of triTestWt in minimaloptix_b200/csrc/gpu/traverse.cuh, operation for
+// operation (this file is compiled with -ffp-contract=off, the GPU side with -fmad=false).  The vertices are
+// sheared and scaled into a space where the ray is the +z axis; the scaled edge functions U, V, W of two triangles
+// sharing an edge are computed from the same operands, so a ray cannot pass between them; exact zeros are decided
+// in double.  No backface culling.  beta / gamma weigh p1 / p2.
+struct WtRay { int kx, ky, kz; float Sx, Sy, Sz; };
+inline float pick3(const float3& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+inline WtRay wtPrep(const float3& d) {
+  WtRay w;
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  w.kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  w.kx = w.kz == 2 ? 0 : w.kz + 1;
+  w.ky = w.kx == 2 ? 0 : w.kx + 1;
+  const float dz = pick3(d, w.kz);
+  if (dz < 0.f) { const int t = w.kx; w.kx = w.ky; w.ky = t; }
+  w.Sx = pick3(d, w.kx) / dz;
+  w.Sy = pick3(d, w.ky) / dz;
+  w.Sz = 1.0f / dz;
+  return w;
+}
+inline bool watertightTriangle(const Ray& ray, const float3& p0, const float3& p1, const float3& p2, float& t, float& beta,
+                               float& gamma) {
+  const WtRay w = wtPrep(ray.direction);
+  const float3 A = p0 - ray.origin, B = p1 - ray.origin, C = p2 - ray.origin;
+  const float Akz = pick3(A, w.kz), Bkz = pick3(B, w.kz), Ckz = pick3(C, w.kz);
+  const float Ax = pick3(A, w.kx) - w.Sx * Akz, Ay = pick3(A, w.ky) - w.Sy * Akz;
+  const float Bx = pick3(B, w.kx) - w.Sx * Bkz, By = pick3(B, w.ky) - w.Sy * Bkz;
+  const float Cx = pick3(C, w.kx) - w.Sx * Ckz, Cy = pick3(C, w.ky) - w.Sy * Ckz;
+  float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+  if (U == 0.f || V == 0.f || W == 0.f) {
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if ((U < 0.f || V < 0.f || W < 0.f) && (U > 0.f || V > 0.f || W > 0.f)) return false;
+  const float det = U + V + W;
+  if (det == 0.f) return false;
+  const float T = U * (w.Sz * Akz) + V * (w.Sz * Bkz) + W * (w.Sz * Ckz);
+  const float rcp = 1.0f / det;
+  t = T * rcp; beta = V * rcp; gamma = W * rcp;
+  return t > ray.tmin;
+}
+
 // Geometry test only (t, beta, gamma, n); attributes are filled by triAttributes for the winner.
 bool hitTriGeom(const orc_ctx& c, const Tri& tr, const Ray& ray, float tmaxCur, float3& n, float& t, float& beta,
                 float& gamma) {  // Geometry.cu:121-134
   const float3 &p0 = c.verts[tr.v[0]], &p1 = c.verts[tr.v[1]], &p2 = c.verts[tr.v[2]];
+  if (c.watertight) {
+    n = cross(p0 - p2, p1 - p0);   // geometric normal as the SDK test leaves it
+    return watertightTriangle(ray, p0, p1, p2, t, beta, gamma) && t < tmaxCur;
+  }
   if (!intersect_triangle(ray, p0, p1, p2, n, t, beta, gamma)) return false;
   return t > ray.tmin && t < tmaxCur;
 }
@@ -758,8 +807,9 @@ int orc_clear_scene(orc_ctx* c) {
   c->built = false;
   return MOX_OK;
 }
-int orc_build_accel(orc_ctx* c, uint32_t, float* out_ms) {
+int orc_build_accel(orc_ctx* c, uint32_t flags, float* out_ms) {
   if (!c) return MOX_ERR_INVALID;
+  c->watertight = (flags & MOX_ACCEL_WATERTIGHT) != 0;
   auto t0 = std::chrono::steady_clock::now();
   buildBvh(*c);
   c->msBuild = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -449,6 +449,27 @@ def test_sorted_ray_queue_is_bit_identical(host, api_tables, gpu_backend, monkey
     assert out[1][3] > out[0][3]    # the sort kernels did run
 
 
+def test_scheduling_variants_are_bit_identical(host, api_tables, gpu_backend, monkeypatch):
+    """How a batch is scheduled must not show in the result: 1 / 2 / 3 sub-batch slices on their own streams,
+    shadow rays on a second stream or in line, the Disney program as one kernel or as light-sampling + BSDF-sampling
+    kernels — same image bit for bit, same ray counts (all read by mox_create)."""
+    sc = host.Scene.builtin("interior", 30000)
+    out = []
+    for slices, overlap, split in (("1", "1", "0"), ("1", "0", "0"), ("2", "1", "0"), ("3", "0", "0"), ("1", "1", "1"), ("2", "0", "1")):
+        monkeypatch.setenv("MOX_SLICES", slices)
+        monkeypatch.setenv("MOX_OVERLAP_SHADOW", overlap)
+        monkeypatch.setenv("MOX_DISNEY_SPLIT", split)
+        g = gpu_backend.context(0)
+        sc.upload(api_tables.gpu, g, 400, 300, 5)
+        g.build_accel()
+        g.render(3, 77)
+        st = g.stats()
+        out.append((g.read_accum(), st["rays_bounce"], st["rays_shadow"]))
+    for o in out[1:]:
+        assert o[1:] == out[0][1:]
+        assert np.array_equal(o[0].view(np.uint32), out[0][0].view(np.uint32))
+
+
 def test_wide_and_binary_traversal_render_identically(host, api_tables, gpu_backend):
     """The acceleration structure must not influence the image: 8-wide vs binary BVH, bit for bit
     (including the order-independent shadow transmittance through GLASS)."""
