@@ -122,7 +122,7 @@ def cpu_sample(args, steps, threads=0):
         per_step.append((rays, dt))
         rays_total += rays
     cores = threads if threads > 0 else (os.cpu_count() or 1)
-    return per_step, {"cores": cores, "kind": "port",
+    return per_step, {"cores": cores, "kind": "port", "triangles": int(sc.info().n_triangles),
                       "sample": f"{w}x{h} (1/16 of the pixels), {steps} spp, same scene/camera/depth/seed schedule, oracle BVH (binned SAH)"}
 
 
@@ -140,7 +140,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(len(timed), 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "triangles": args.tris, "sample": info["sample"]},
+            "config": {"workload": WORKLOAD, "triangles": info["triangles"], "sample": info["sample"]},
             "cpu_baseline": dict(info, value=value, unit="Mrays/s"),
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -281,9 +281,44 @@ def main():
         dist.all_reduce(ce, op=dist.ReduceOp.SUM)
     e2e_value = ce.item() / te.item() / 1e6
 
-    # ---- counting pass for the algorithmic bytes of the traversal kernels (untimed)
-    roofline = roofline_shadow = None
+    # ---- serial pass (rank 0, untimed for `value`): the same steps on a context whose launches do not overlap
+    # (MOX_OVERLAP_SHADOW=0, one slice), so a CUDA-event span on the launching stream is one kernel alone on the
+    # GPU.  The timed region above runs the shadow launch of bounce b next to the extend launch of bounce b+1;
+    # there the spans of the two overlap and do not add up to the step.
+    roofline = roofline_shadow = roofline_build = per_depth = None
+    serial = None
     if rank == 0:
+        saved = {k: os.environ.get(k) for k in ("MOX_OVERLAP_SHADOW", "MOX_SLICES")}
+        os.environ["MOX_OVERLAP_SHADOW"], os.environ["MOX_SLICES"] = "0", "1"
+        sctx = mox.gpu().context(local)
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        sc.upload(api, sctx, W, H, MAX_DEPTH)
+        sctx.set_partition(rank, world, TILE)
+        if args.emulate_world > 1 and world == 1:
+            sctx.set_partition(0, args.emulate_world, TILE)
+        sctx.build_accel()
+        sctx.render(SPP_PER_STEP, SEED)
+        q0 = sctx.stats()
+        n_serial = max(1, min(args.steps, 4))
+        for _ in range(n_serial):
+            sctx.render(SPP_PER_STEP, SEED)
+        q1 = sctx.stats()
+        dd = lambda k: [b - a for a, b in zip(q0[k], q1[k])]
+        serial = {"steps": n_serial, "ms_per_step": (q1["ms_render"] - q0["ms_render"]) / n_serial,
+                  "stage_ms_per_step": {k: (q1[k] - q0[k]) / n_serial for k in ("ms_generate", "ms_extend", "ms_shade", "ms_shadow", "ms_accumulate")}}
+        rays_d, sh_d, ms_e, ms_s = dd("rays_depth"), dd("shadow_traced_depth"), dd("ms_extend_depth"), dd("ms_shadow_depth")
+        per_depth = [{"depth": d, "rays": int(rays_d[d]), "ms_extend": ms_e[d], "extend_mrays_per_s": rays_d[d] / (ms_e[d] * 1e3) if ms_e[d] > 0 else None,
+                      "shadow_rays_traversed": int(sh_d[d]), "ms_shadow": ms_s[d], "shadow_mrays_per_s": sh_d[d] / (ms_s[d] * 1e3) if ms_s[d] > 0 else None}
+                     for d in range(1, 8) if rays_d[d]]
+        b_rays, b_ms = sum(rays_d[2:]), sum(ms_e[2:])
+        serial["bounce_only_extend_mrays_per_s"] = b_rays / (b_ms * 1e3) if b_ms > 0 else None   # traversal kernel alone, depth >= 2
+        serial["primary_extend_mrays_per_s"] = rays_d[1] / (ms_e[1] * 1e3) if ms_e[1] > 0 else None
+
+        # ---- counting pass for the algorithmic bytes of the traversal kernels (untimed)
         cctx = mox.gpu().context(local)
         sc.upload(api, cctx, W, H, MAX_DEPTH)
         cctx.set_partition(rank, world, TILE)
@@ -296,37 +331,50 @@ def main():
         except Exception:
             pass
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json, HBM copy)" if "hbm_gbs" in peaks else "fallback"
+        peak_src = "measured (MEASURED_PEAKS.json, HBM copy)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
-        def roof(kernel, key, rays_counted, nodes, prims, fixed_bytes, rays_timed, ms, launches):
+        def roof(kernel, key, rays_counted, nodes, prims, fixed_bytes, fixed_note, rays_timed, ms, launches, ms_overlapped):
             n_node, n_prim = nodes / max(rays_counted, 1), prims / max(rays_counted, 1)
             b_ray = fixed_bytes + n_node * cs["node_bytes"] + n_prim * cs["prim_bytes"]
             achieved = rays_timed * b_ray / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             t = traffic.get(key, {})
             return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": t.get("dram_bytes_per_launch"),
-                    "traffic_note": "dram__bytes_read+write per launch from the committed ncu --set full capture (1 spp per wavefront; "
-                                    "this run batches %d spp per launch)" % SPP_PER_STEP if t else None,
-                    "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim, "node_bytes": cs["node_bytes"],
+                    "l2_bytes_per_launch": t.get("lts_bytes_per_launch"), "l2_gbs_under_ncu": t.get("lts_gbs_under_ncu"),
+                    "traffic_note": traffic.get("_source") if t else None,
+                    "bytes_per_ray": b_ray, "fixed_bytes_per_ray": fixed_bytes, "fixed_bytes_note": fixed_note,
+                    "nodes_per_ray": n_node, "prims_per_ray": n_prim, "node_bytes": cs["node_bytes"],
                     "prim_bytes": cs["prim_bytes"], "rays_per_s": rays_timed / (ms * 1e-3) if ms > 0 else 0.0,
-                    "launches": launches, "avg_launch_ms": ms / max(launches, 1),
-                    "share_of_step": ms / max(s1["ms_render"] - s0["ms_render"], 1e-9),
-                    "note": "BVH + triangles are L2-resident (126 MB L2): the algorithmic bytes are served by L2, DRAM traffic is far "
-                            "smaller; ncu shows the kernel latency/issue-bound (profiles/r1_g_kernels_summary.txt)"}
+                    "launches": launches, "avg_launch_ms": ms / max(launches, 1), "rays_per_launch": rays_timed / max(launches, 1),
+                    "timing": "CUDA events on the launching stream, %d steps of the serial pass (kernel alone on the GPU)" % n_serial,
+                    "avg_launch_ms_in_timed_region": ms_overlapped,
+                    "share_of_step": ms / max(q1["ms_render"] - q0["ms_render"], 1e-9),
+                    "note": "BVH + triangles are L2-resident (126 MB L2): the algorithmic bytes are served by L1/L2, DRAM traffic is far "
+                            "smaller; ncu shows the kernel latency/issue-bound (profiles/README.md)"}
 
-        own_rays = rays_of(s1) - rays_of(s0)
-        own_shadow = s1["rays_shadow_traced"] - s0["rays_shadow_traced"]
-        sh_ms = s1["ms_shadow"] - s0["ms_shadow"]
-        # closest hit: 32 B ray + 16 B hit; shadow: 32 B ray + 16 B contribution read + 16 B written
-        roofline = roof("k_traverse<closest> (extend rays)", "k_traverse_closest", rays_of(cs), cs["node_visits"], cs["prim_tests"], 48,
-                        own_rays, ext_ms, ext_launches)
-        roofline_shadow = roof("k_traverse<anyhit> (shadow rays)", "k_traverse_shadow", cs["rays_shadow_traced"], cs["node_visits_shadow"],
-                               cs["prim_tests_shadow"], 64, own_shadow, sh_ms, ext_launches)
-        del cctx
+        launches_s = q1["extend_launches"] - q0["extend_launches"]
+        # extend ray: 32 B ray + 16 B hit.  Shadow ray: 32 B ray + 4 B queue entry, + 16 B for a blocked ray
+        # (one store of its contribution) and 32 B for a tinted one (load + store), by their counted shares.
+        traced = max(cs["rays_shadow_traced"], 1)
+        f_blk, f_tnt = cs["rays_shadow_blocked"] / traced, cs["rays_shadow_tinted"] / traced
+        roofline = roof("k_traverse_wide<closest> (extend rays)", "k_traverse_closest", rays_of(cs), cs["node_visits"], cs["prim_tests"], 48,
+                        "32 ray + 16 hit", rays_of(q1) - rays_of(q0), q1["ms_extend"] - q0["ms_extend"], launches_s,
+                        ext_ms / max(ext_launches, 1))
+        roofline_shadow = roof("k_traverse_wide<anyhit> (shadow rays)", "k_traverse_shadow", cs["rays_shadow_traced"], cs["node_visits_shadow"],
+                               cs["prim_tests_shadow"], 36 + 16 * f_blk + 32 * f_tnt,
+                               "32 ray + 4 queue + 16 x %.3f blocked + 32 x %.3f tinted" % (f_blk, f_tnt),
+                               q1["rays_shadow_traced"] - q0["rays_shadow_traced"], q1["ms_shadow"] - q0["ms_shadow"], launches_s,
+                               (s1["ms_shadow"] - s0["ms_shadow"]) / max(ext_launches, 1))
+        b_bytes = 450.0 * info.n_triangles
+        roofline_build = {"bound": "hbm", "kernel": "mox_build_accel (Morton + onesweep sort + PLOC + SAH-optimal collapse + pack)",
+                          "achieved": b_bytes / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                          "frac": b_bytes / (build_ms * 1e-3) / 1e9 / peak if build_ms > 0 else 0.0, "bytes_per_triangle": 450,
+                          "triangles": int(info.n_triangles), "ms": build_ms, "traffic": None}
+        del cctx, sctx
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -346,7 +394,8 @@ def main():
                 "wall_ms_per_step": wall_ms / args.steps, "stage_ms": stage_ms,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 76 + 4, "d2h_bytes_per_step": int(d2h)},
                 "gather_bytes": tiles.bytes_on_the_wire(), "gather_transport": tiles.transport(), "gather_ms": g0.elapsed_time(g1), "render_ms_rank0": s1["ms_render"] - s0["ms_render"], "render_ms_per_rank": render_per_rank, "tile": TILE, "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline_shadow if (roofline_shadow and roofline and roofline_shadow["share_of_step"] > roofline["share_of_step"]) else roofline,
-                "roofline_closest": roofline, "roofline_shadow": roofline_shadow, "cpu_baseline": cpu_baseline}
+                "roofline_closest": roofline, "roofline_shadow": roofline_shadow, "roofline_build": roofline_build,
+                "serial_pass": serial, "per_depth": per_depth, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

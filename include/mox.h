@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MOX_ABI_VERSION 2
+#define MOX_ABI_VERSION 3
 
 typedef struct mox_ctx mox_ctx; /* opaque */
 
@@ -91,6 +91,14 @@ typedef struct mox_stats {
   uint64_t node_visits_shadow; /* shadow-ray traversal, only with MOX_ACCEL_COUNTERS      */
   uint64_t prim_tests_shadow;
   uint64_t rays_shadow_traced; /* shadow rays with a non-zero contribution (the ones traversed) */
+  /* traversed shadow rays that touched their 16-byte contribution record: blocked (one store) or tinted by
+   * Disney GLASS (load + store); the others finish without a write.  Only with MOX_ACCEL_COUNTERS. */
+  uint64_t rays_shadow_blocked, rays_shadow_tinted;
+  /* per path depth d = 1 (camera rays) .. MOX_STATS_DEPTHS-1 (deeper bounces are added to the last entry; entry 0
+   * is unused): closest-hit rays traced, shadow rays traversed, and the device time of the two traversal launches */
+#define MOX_STATS_DEPTHS 8
+  uint64_t rays_depth[MOX_STATS_DEPTHS], shadow_traced_depth[MOX_STATS_DEPTHS];
+  double ms_extend_depth[MOX_STATS_DEPTHS], ms_shadow_depth[MOX_STATS_DEPTHS];
 } mox_stats;
 
 /* ---- context ------------------------------------------------------------- */

@@ -10,7 +10,7 @@
 struct DeviceArena {
   char* base = nullptr;
   size_t cap = 0, off = 0;
-  unsigned long long* pinned = nullptr;  // 8 bytes of pinned host memory for small read-backs
+  unsigned long long* pinned = nullptr;  // 64 bytes of pinned host memory for small read-backs
   bool reserve(size_t bytes) {
     off = 0;
     if (bytes <= cap) return true;
@@ -48,6 +48,7 @@ struct BuildInput {
 };
 
 // Scratch of the PLOC hierarchy builder (ploc.cu), allocated before the timed build.
+struct PlocState;
 struct PlocScratch {
   uint32_t* cid[2] = {nullptr, nullptr};
   float4 *cLo[2] = {nullptr, nullptr}, *cHi[2] = {nullptr, nullptr};
@@ -56,6 +57,7 @@ struct PlocScratch {
   uint2* children = nullptr;
   uint32_t *parent = nullptr, *size = nullptr, *leafPos = nullptr, *orderedIds = nullptr;
   unsigned long long* tileSums = nullptr;
+  PlocState* state = nullptr;               // loop state, one slot per iteration (ploc.cu)
   unsigned long long* hostTotal = nullptr;  // pinned
 };
 size_t plocScratchBytes(int n);

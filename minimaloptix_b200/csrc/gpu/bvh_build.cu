@@ -399,7 +399,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
     out = fresh;
   }
   DeviceArena& arena = *in.arena;
-  if (!arena.pinned && cudaMallocHost(&arena.pinned, 8) != cudaSuccess) { err = "cudaMallocHost failed"; return false; }
+  if (!arena.pinned && cudaMallocHost(&arena.pinned, 64) != cudaSuccess) { err = "cudaMallocHost failed"; return false; }
   // persistent outputs: reuse the previous build's buffers when they are large enough
   auto ensureOut = [&](size_t nodesNeeded, size_t packedNeeded) -> bool {
     if (out.nodesCap < nodesNeeded || !out.nodes) {

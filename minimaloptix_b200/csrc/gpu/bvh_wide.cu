@@ -113,10 +113,11 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
                  const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi, const uint32_t* __restrict__ size,
                  const uint32_t* __restrict__ parent, const uint32_t* __restrict__ leafPos, uint32_t root,
                  const uint32_t* __restrict__ orderedIds, BvhNode8* __restrict__ out, uint32_t* __restrict__ orderedIds8,
-                 WorkItem* __restrict__ nextItems, uint32_t* __restrict__ counters /* [0] nodes, [1] prims, [2] next items */,
+                 WorkItem* __restrict__ nextItems, uint32_t* __restrict__ counters /* [0] nodes, [1] prims */,
+                 const uint32_t* __restrict__ levelCount /* items of this level; [1]: of the next, filled here */,
                  const uint32_t* __restrict__ decision /* null: greedy collapse */) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nItems) return;
+  if (w >= nItems || w >= (int)__ldg(levelCount)) return;   // nItems: the host's upper bound (grid size)
   const WorkItem it = items[w];
   uint32_t ch[8];
   int n = 0;
@@ -211,7 +212,7 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
   }
   const uint32_t childBase = nInner ? atomicAdd(&counters[0], nInner) : 0u;
   const uint32_t primBase = nPrims ? atomicAdd(&counters[1], nPrims) : 0u;
-  const uint32_t nextBase = nInner ? atomicAdd(&counters[2], nInner) : 0u;
+  const uint32_t nextBase = nInner ? atomicAdd(const_cast<uint32_t*>(levelCount) + 1, nInner) : 0u;
   // ---- emit
   uint32_t meta[8], qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
   uint32_t innerRank = 0, primOff = 0;
@@ -270,9 +271,9 @@ inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 #define WCK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 size_t wideScratchBytes(int n) {
-  // two work queues of at most n/2 items (8 B each), 4 counters, the wide-leaf order; slack for alignment
+  // two work queues of at most n/2 items (8 B each), 4 counters, 258 level counts, the wide-leaf order; slack for alignment
   // + the collapse programme: 2 float4 of costs, one decision word and one arrival counter per inner binary node
-  return (size_t)std::max(n, 2) * (8 + 8 + 4 + 32 + 4 + 4) + 8 * 256 + 1024;
+  return (size_t)std::max(n, 2) * (8 + 8 + 4 + 32 + 4 + 4) + 9 * 256 + 1024 + 2048;   // + the per-level item counts
 }
 
 // Collapse the PLOC tree held in `s` (n >= 2 leaves) into outNodes (capacity >= n wide nodes) and
@@ -295,27 +296,41 @@ bool wideCollapse(const PlocScratch& s, int n, uint32_t root, DeviceArena& arena
     k_collapse_dp<<<divUp(n, 128), 128, 0, stream>>>(n, root, s.children, s.parent, s.nodeLo, s.nodeHi, s.size, cost, dec, arrivals);
     decision = dec;
   }
-  uint32_t init[4] = {1u, 0u, 0u, 0u};  // node 0 is the root
-  WorkItem rootItem{root, 0u};
-  WCK(cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, stream));
-  WCK(cudaMemcpyAsync(q[0], &rootItem, sizeof rootItem, cudaMemcpyHostToDevice, stream));
-  int cur = 0, count = 1, levels = 0;
-  while (count > 0) {
-    k_collapse_level<<<divUp(count, 128), 128, 0, stream>>>(count, q[cur], n, s.children, s.nodeLo, s.nodeHi, s.size, s.parent, s.leafPos,
-                                                           root, s.orderedIds, outNodes, orderedIds8, q[cur ^ 1], counters, decision);
-    uint32_t host[4];
-    WCK(cudaMemcpyAsync(host, counters, sizeof host, cudaMemcpyDeviceToHost, stream));
+  // Level by level, the item count of each level kept on the device (levelCount[l], filled by level l-1): the host
+  // enqueues kLevelBatch levels back to back with grids sized for the most a level can hold (8x the level before,
+  // never more than n/2 inner nodes) and reads the counts back once per batch.
+  constexpr int kMaxLevels = 256, kLevelBatch = 4;
+  uint32_t* levelCount = arena.take<uint32_t>(kMaxLevels + 2);
+  if (!levelCount) { err = "wide-BVH scratch does not fit the build arena"; return false; }
+  WCK(cudaMemsetAsync(levelCount, 0, (kMaxLevels + 2) * 4, stream));
+  uint32_t* host = (uint32_t*)arena.pinned;   // 64 pinned bytes: [0..3] counters, [4..8] counts of a batch of levels
+  host[0] = 1u; host[1] = 0u; host[2] = 0u; host[3] = 0u;   // node 0 is the root
+  host[4] = 1u;
+  WorkItem* rootItem = (WorkItem*)(host + 8);
+  *rootItem = WorkItem{root, 0u};
+  WCK(cudaMemcpyAsync(counters, host, 16, cudaMemcpyHostToDevice, stream));
+  WCK(cudaMemcpyAsync(levelCount, host + 4, 4, cudaMemcpyHostToDevice, stream));
+  WCK(cudaMemcpyAsync(q[0], rootItem, sizeof(WorkItem), cudaMemcpyHostToDevice, stream));
+  int cur = 0, levels = 0;
+  size_t bound = 1;   // upper bound of the items of level `levels`
+  for (bool more = true; more;) {
+    if (levels + kLevelBatch >= kMaxLevels) { err = "wide collapse did not terminate"; return false; }
+    for (int b = 0; b < kLevelBatch; ++b, ++levels) {
+      k_collapse_level<<<divUp(bound, 128), 128, 0, stream>>>((int)bound, q[cur], n, s.children, s.nodeLo, s.nodeHi, s.size, s.parent, s.leafPos,
+                                                             root, s.orderedIds, outNodes, orderedIds8, q[cur ^ 1], counters, levelCount + levels, decision);
+      cur ^= 1;
+      bound = std::min<size_t>(bound * 8, (size_t)std::max(n / 2, 1));
+    }
+    WCK(cudaMemcpyAsync(host, counters, 16, cudaMemcpyDeviceToHost, stream));
+    WCK(cudaMemcpyAsync(host + 4, levelCount + levels - kLevelBatch + 1, kLevelBatch * 4, cudaMemcpyDeviceToHost, stream));
     WCK(cudaStreamSynchronize(stream));
-    count = (int)host[2];
-    uint32_t zero = 0;
-    WCK(cudaMemcpyAsync(counters + 2, &zero, 4, cudaMemcpyHostToDevice, stream));
-    cur ^= 1;
-    if (++levels > 4096) { err = "wide collapse did not terminate"; return false; }
     *nNodesOut = (int)host[0];
     if ((int)host[1] > n) { err = "wide collapse emitted too many primitives"; return false; }
+    // the first empty level ends the tree (the levels enqueued after it did nothing)
+    for (int b = 0; b < kLevelBatch; ++b)
+      if (host[4 + b] == 0u) { more = false; levels = levels - kLevelBatch + 1 + b; break; }
+    if (more) bound = std::min<size_t>(bound, (size_t)host[4 + kLevelBatch - 1] );
   }
-  uint32_t host[4];
-  WCK(cudaMemcpy(host, counters, sizeof host, cudaMemcpyDeviceToHost));
   if ((int)host[1] != n) { err = "wide collapse lost primitives (" + std::to_string(host[1]) + " of " + std::to_string(n) + ")"; return false; }
   WCK(cudaGetLastError());
   *orderedIds8Out = orderedIds8;

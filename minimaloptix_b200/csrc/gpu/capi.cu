@@ -25,7 +25,7 @@ enum Stage { ST_GENERATE = 0, ST_EXTEND, ST_SHADE, ST_SHADOW, ST_ACCUMULATE, ST_
 // Event pairs around the kernels of each stage; summed after the batch's final synchronize.
 struct StageTimer {
   std::vector<cudaEvent_t> pool;
-  struct Span { int stage; size_t e0, e1; };
+  struct Span { int stage; size_t e0, e1; uint32_t depth; };
   std::vector<Span> spans;
   size_t used = 0;
   size_t grab(cudaStream_t s) {
@@ -33,10 +33,16 @@ struct StageTimer {
     cudaEventRecord(pool[used], s);
     return used++;
   }
-  void begin(int stage, cudaStream_t s) { spans.push_back({stage, grab(s), 0}); }
+  void begin(int stage, cudaStream_t s, uint32_t depth = 0) { spans.push_back({stage, grab(s), 0, depth}); }
   void end(cudaStream_t s) { spans.back().e1 = grab(s); }
-  void collect(double* ms) {
-    for (auto& sp : spans) { float t = 0; if (cudaEventElapsedTime(&t, pool[sp.e0], pool[sp.e1]) == cudaSuccess) ms[sp.stage] += t; }
+  // msDepth[stage == ST_SHADOW][d]: the two traversal launches per path depth (mox_stats.ms_extend_depth / ms_shadow_depth)
+  void collect(double* ms, double (*msDepth)[MOX_STATS_DEPTHS]) {
+    for (auto& sp : spans) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, pool[sp.e0], pool[sp.e1]) != cudaSuccess) continue;
+      ms[sp.stage] += t;
+      if (sp.depth) msDepth[sp.stage == ST_SHADOW ? 1 : 0][std::min<uint32_t>(sp.depth, MOX_STATS_DEPTHS - 1)] += t;
+    }
     spans.clear(); used = 0;
   }
   void release() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); }
@@ -143,7 +149,9 @@ struct mox_ctx {
 
   // stats
   uint64_t raysPrimary = 0, raysBounce = 0, raysShadow = 0, nonfinite = 0, launches = 0, nodeVisits = 0, primTests = 0;
-  uint64_t nodeVisitsShadow = 0, primTestsShadow = 0, raysShadowTraced = 0;
+  uint64_t nodeVisitsShadow = 0, primTestsShadow = 0, raysShadowTraced = 0, shadowBlocked = 0, shadowTinted = 0;
+  uint64_t raysDepth[MOX_STATS_DEPTHS] = {}, shadowDepth[MOX_STATS_DEPTHS] = {};
+  double msDepth[2][MOX_STATS_DEPTHS] = {};   // [0] extend, [1] shadow traversal launches per path depth
   double msRender = 0, msBuild = 0;
   double msStage[ST_COUNT] = {0, 0, 0, 0, 0};
   uint64_t extendLaunches = 0, kernelLaunches = 0;
@@ -399,7 +407,7 @@ int sliceEnqueueExtend(mox_ctx* c, mox_ctx::Slice& sl) {
   // bounce 1 traces exactly `bound` camera rays; later bounces read the number of spawned rays from the previous
   // bounce's counter block, `bound` (what was shaded) only sizes the grids
   const uint32_t* countPtr = depth == 1 ? nullptr : bounceBlock(sl.pb, depth - 1) + C_NEXT;
-  tm.begin(ST_EXTEND, sl.stream);
+  tm.begin(ST_EXTEND, sl.stream, depth);
   launchExtend(lc, lc.pb.qCur, sl.bound, countPtr, depth);
   tm.end(sl.stream);
   tm.begin(ST_SHADE, sl.stream);
@@ -432,11 +440,14 @@ int sliceAdvance(mox_ctx* c, mox_ctx::Slice& sl) {
   PathBuffers& pb = sl.pb;
   const uint32_t depth = sl.depth;
   const uint32_t* hostBounce = sl.hostCnt + C_WORDS + (depth % BOUNCE_RING) * C_BOUNCE_WORDS;
-  if (depth == 1) c->raysPrimary += sl.bound;
+  const uint32_t dIdx = std::min<uint32_t>(depth, MOX_STATS_DEPTHS - 1);
+  if (depth == 1) { c->raysPrimary += sl.bound; c->raysDepth[1] += sl.bound; }
   else {  // exact number of rays this bounce traced, and of shadow rays the previous one queued
     const uint32_t* prev = sl.hostCnt + C_WORDS + ((depth - 1) % BOUNCE_RING) * C_BOUNCE_WORDS;
     c->raysBounce += prev[C_NEXT];
     c->raysShadowTraced += prev[C_SHQ];
+    c->raysDepth[dIdx] += prev[C_NEXT];
+    c->shadowDepth[std::min<uint32_t>(depth - 1, MOX_STATS_DEPTHS - 1)] += prev[C_SHQ];
   }
   uint32_t any = 0;
   for (int k = 0; k < Q_COUNT; ++k) { sl.matCount[k] = hostBounce[C_MAT0 + k]; any += sl.matCount[k]; }
@@ -456,7 +467,7 @@ int sliceAdvance(mox_ctx* c, mox_ctx::Slice& sl) {
       CUCK(c, cudaEventRecord(sl.evShaded, sl.stream));
       CUCK(c, cudaStreamWaitEvent(ss, sl.evShaded, 0));
     }
-    tm.begin(ST_SHADOW, ss);
+    tm.begin(ST_SHADOW, ss, depth);
     launchShadow(lc, sl.matCount[Q_DISNEY], ss);
     tm.end(ss);
     tm.begin(ST_SHADE, ss);
@@ -581,8 +592,9 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     CUCK(c, cudaEventSynchronize(sl.evReady));
     if (k) CUCK(c, cudaStreamWaitEvent(c->stream, sl.evReady, 0));
     const uint32_t* host = sl.hostCnt;
-    sl.timer.collect(c->msStage);
+    sl.timer.collect(c->msStage, c->msDepth);
     c->nonfinite += host[C_NONFINITE];
+    c->shadowBlocked += host[C_SH_BLOCKED]; c->shadowTinted += host[C_SH_TINTED];
     c->raysShadow += host[C_SHADOW];
     c->nodeVisits += ((uint64_t)host[C_NODEVIS_HI] << 32) | host[C_NODEVIS_LO];
     c->primTests += ((uint64_t)host[C_PRIMTEST_HI] << 32) | host[C_PRIMTEST_LO];
@@ -1242,9 +1254,10 @@ int mox_clear_accum(mox_ctx* c) {
   if (c->dAccu) CUCK(c, cudaMemsetAsync(c->dAccu, 0, (size_t)c->accuW * c->accuH * 12, c->stream));
   CUCK(c, cudaStreamSynchronize(c->stream));
   c->launches = 0; c->raysPrimary = c->raysBounce = c->raysShadow = c->nonfinite = c->nodeVisits = c->primTests = 0;
-  c->nodeVisitsShadow = c->primTestsShadow = c->raysShadowTraced = 0;
+  c->nodeVisitsShadow = c->primTestsShadow = c->raysShadowTraced = c->shadowBlocked = c->shadowTinted = 0;
   c->msRender = 0;
   for (double& m : c->msStage) m = 0;
+  for (int d = 0; d < MOX_STATS_DEPTHS; ++d) { c->raysDepth[d] = c->shadowDepth[d] = 0; c->msDepth[0][d] = c->msDepth[1][d] = 0; }
   c->extendLaunches = c->kernelLaunches = 0;
   return MOX_OK;
 }
@@ -1340,6 +1353,11 @@ int mox_get_stats(mox_ctx* c, mox_stats* s) {
   s->extend_launches = c->extendLaunches; s->kernel_launches = c->kernelLaunches;
   s->node_visits_shadow = c->nodeVisitsShadow; s->prim_tests_shadow = c->primTestsShadow;
   s->rays_shadow_traced = c->raysShadowTraced;
+  s->rays_shadow_blocked = c->shadowBlocked; s->rays_shadow_tinted = c->shadowTinted;
+  for (int d = 0; d < MOX_STATS_DEPTHS; ++d) {
+    s->rays_depth[d] = c->raysDepth[d]; s->shadow_traced_depth[d] = c->shadowDepth[d];
+    s->ms_extend_depth[d] = c->msDepth[0][d]; s->ms_shadow_depth[d] = c->msDepth[1][d];
+  }
   return MOX_OK;
 }
 

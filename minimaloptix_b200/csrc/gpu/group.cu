@@ -173,6 +173,12 @@ int groupStats(mox_group* g, mox_stats* out) {
     acc.rays_primary += s.rays_primary; acc.rays_bounce += s.rays_bounce; acc.rays_shadow += s.rays_shadow;
     acc.nonfinite_samples += s.nonfinite_samples; acc.node_visits += s.node_visits; acc.prim_tests += s.prim_tests;
     acc.node_visits_shadow += s.node_visits_shadow; acc.prim_tests_shadow += s.prim_tests_shadow;
+    acc.rays_shadow_blocked += s.rays_shadow_blocked; acc.rays_shadow_tinted += s.rays_shadow_tinted;
+    for (int d = 0; d < MOX_STATS_DEPTHS; ++d) {
+      acc.rays_depth[d] += s.rays_depth[d]; acc.shadow_traced_depth[d] += s.shadow_traced_depth[d];
+      acc.ms_extend_depth[d] = acc.ms_extend_depth[d] > s.ms_extend_depth[d] ? acc.ms_extend_depth[d] : s.ms_extend_depth[d];
+      acc.ms_shadow_depth[d] = acc.ms_shadow_depth[d] > s.ms_shadow_depth[d] ? acc.ms_shadow_depth[d] : s.ms_shadow_depth[d];
+    }
     acc.rays_shadow_traced += s.rays_shadow_traced; acc.extend_launches += s.extend_launches; acc.kernel_launches += s.kernel_launches;
     // devices run side by side: times are the slowest device's
     acc.ms_render = acc.ms_render > s.ms_render ? acc.ms_render : s.ms_render;

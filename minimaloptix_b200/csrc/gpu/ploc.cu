@@ -19,6 +19,17 @@ constexpr int PL_THREADS = 256;
 constexpr int PL_ITEMS = 4;
 constexpr int PL_TILE = PL_THREADS * PL_ITEMS;
 constexpr int PL_MAX_RADIUS = 128;
+constexpr int PL_TAIL = 1024;      // at most this many clusters: the single-block kernel finishes the tree
+constexpr int PL_MAX_ITERS = 250;  // state slots (a 10 M-primitive build takes ~40 iterations)
+constexpr int PL_BATCH = 8;        // iterations enqueued between two host read-backs
+
+// Loop state of the clustering, one slot per iteration, in device memory: iteration `it` reads slot it and its scan
+// kernel writes slot it+1, so the host can enqueue PL_BATCH iterations back to back — grids sized for the last
+// count it knows (counts only shrink; surplus blocks return at once) — and read one slot back per batch instead of
+// one count per iteration.  An iteration whose slot says count <= PL_TAIL does nothing.
+}  // namespace
+struct PlocState { int count; uint32_t nodeBase; uint32_t iters; uint32_t pad; };
+namespace {
 
 __device__ __forceinline__ float mergedArea(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi) {
   float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
@@ -43,9 +54,11 @@ __global__ void k_ploc_init(int n, const uint32_t* __restrict__ sortedIds, const
 }
 
 // nearest neighbour of cluster i among [i - radius, i + radius]; ties -> smaller index.
-__global__ void __launch_bounds__(PL_THREADS) k_ploc_nn(int n, int radius, const float4* __restrict__ cLo,
+__global__ void __launch_bounds__(PL_THREADS) k_ploc_nn(const PlocState* __restrict__ st, int radius, const float4* __restrict__ cLo,
                                                         const float4* __restrict__ cHi, uint32_t* __restrict__ nn) {
   __shared__ float4 sLo[PL_THREADS + 2 * PL_MAX_RADIUS], sHi[PL_THREADS + 2 * PL_MAX_RADIUS];
+  const int n = st->count;
+  if (n <= PL_TAIL || blockIdx.x * PL_THREADS >= n) return;
   const int base = blockIdx.x * PL_THREADS - radius;
   for (int k = threadIdx.x; k < PL_THREADS + 2 * radius; k += PL_THREADS) {
     int j = base + k;
@@ -86,9 +99,11 @@ __device__ __forceinline__ unsigned long long blockReduce(unsigned long long v, 
   return t;
 }
 
-__global__ void __launch_bounds__(PL_THREADS) k_ploc_tile_sums(int n, const uint32_t* __restrict__ nn,
+__global__ void __launch_bounds__(PL_THREADS) k_ploc_tile_sums(const PlocState* __restrict__ st, const uint32_t* __restrict__ nn,
                                                                unsigned long long* __restrict__ tileSums) {
   __shared__ unsigned long long sh[PL_THREADS / 32];
+  const int n = st->count;
+  if (n <= PL_TAIL || blockIdx.x * PL_TILE >= n) return;
   unsigned long long v = 0;
   int base = blockIdx.x * PL_TILE + threadIdx.x * PL_ITEMS;
 #pragma unroll
@@ -97,10 +112,13 @@ __global__ void __launch_bounds__(PL_THREADS) k_ploc_tile_sums(int n, const uint
   if (threadIdx.x == 0) tileSums[blockIdx.x] = t;
 }
 
-// single block: exclusive scan of the tile sums in place; total -> *total
-__global__ void __launch_bounds__(1024) k_ploc_scan_tiles(int nTiles, unsigned long long* __restrict__ tileSums,
-                                                          unsigned long long* __restrict__ total) {
+// single block: exclusive scan of the tile sums in place; the totals (clusters left, nodes created) advance the
+// loop state: st[0] is this iteration's slot, st[1] the next one's
+__global__ void __launch_bounds__(1024) k_ploc_scan_tiles(PlocState* __restrict__ st, unsigned long long* __restrict__ tileSums) {
   __shared__ unsigned long long sh[1024];
+  const int n = st->count;
+  if (n <= PL_TAIL) { if (threadIdx.x == 0) st[1] = st[0]; return; }
+  const int nTiles = (n + PL_TILE - 1) / PL_TILE;
   unsigned long long carry = 0;
   for (int base = 0; base < nTiles; base += 1024) {
     int i = base + threadIdx.x;
@@ -117,18 +135,28 @@ __global__ void __launch_bounds__(1024) k_ploc_scan_tiles(int nTiles, unsigned l
     carry += sh[1023];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  if (threadIdx.x == 0) {
+    PlocState nx;
+    nx.count = (int)(carry & 0xffffffffull);
+    nx.nodeBase = st->nodeBase + (uint32_t)(carry >> 32);
+    nx.iters = st->iters + 1u;
+    nx.pad = 0u;
+    st[1] = nx;
+  }
 }
 
 // merge mutual pairs and compact: new cluster arrays, new inner nodes
 __global__ void __launch_bounds__(PL_THREADS)
-k_ploc_merge(int n, int nLeaves, uint32_t nodeBase, const uint32_t* __restrict__ nn, const unsigned long long* __restrict__ tileOffsets,
+k_ploc_merge(const PlocState* __restrict__ st, int nLeaves, const uint32_t* __restrict__ nn, const unsigned long long* __restrict__ tileOffsets,
              const uint32_t* __restrict__ cidIn, const float4* __restrict__ cLoIn, const float4* __restrict__ cHiIn,
              uint32_t* __restrict__ cidOut, float4* __restrict__ cLoOut, float4* __restrict__ cHiOut,
              float4* __restrict__ nodeLo, float4* __restrict__ nodeHi, uint2* __restrict__ children, uint32_t* __restrict__ parent,
              uint32_t* __restrict__ size) {
   __shared__ unsigned long long sh[PL_THREADS / 32];
   __shared__ unsigned long long warpOff[PL_THREADS / 32];
+  const int n = st->count;
+  if (n <= PL_TAIL || blockIdx.x * PL_TILE >= n) return;
+  const uint32_t nodeBase = st->nodeBase;
   const int base = blockIdx.x * PL_TILE + threadIdx.x * PL_ITEMS;
   unsigned long long f[PL_ITEMS], v = 0;
 #pragma unroll
@@ -177,7 +205,6 @@ k_ploc_merge(int n, int nLeaves, uint32_t nodeBase, const uint32_t* __restrict__
 // All remaining iterations once at most PL_TAIL clusters are left: one block, clusters in shared
 // memory, no host round trips.  Same merge rule and the same scan-based node numbering as the
 // multi-kernel iterations above.
-constexpr int PL_TAIL = 1024;
 __global__ void __launch_bounds__(PL_TAIL)
 k_ploc_tail(int n, int nLeaves, int radius, uint32_t nodeBase, const uint32_t* __restrict__ cidIn, const float4* __restrict__ cLoIn,
             const float4* __restrict__ cHiIn, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi, uint2* __restrict__ children,
@@ -322,7 +349,7 @@ size_t plocScratchBytes(int n) {
   const size_t nn = (size_t)std::max(n, 2);
   // 2 cid + nn + parent(2) + size(2) + leafPos + orderedIds = 9 words, 4 cluster boxes + 2x2 node boxes = 8 float4,
   // children 8 B, tile sums; plus alignment slack for 16 slices
-  return nn * (9 * 4 + 8 * 16 + 8) + (size_t)(divUp(nn, PL_TILE) + 2) * 8 + 16 * 256;
+  return nn * (9 * 4 + 8 * 16 + 8) + (size_t)(divUp(nn, PL_TILE) + 2) * 8 + (size_t)(PL_MAX_ITERS + 1) * sizeof(PlocState) + 17 * 256;
 }
 
 bool plocAlloc(PlocScratch& s, int n, DeviceArena& a, std::string& err) {
@@ -336,8 +363,9 @@ bool plocAlloc(PlocScratch& s, int n, DeviceArena& a, std::string& err) {
   s.parent = a.take<uint32_t>(2 * nn); s.size = a.take<uint32_t>(2 * nn);
   s.leafPos = a.take<uint32_t>(nn); s.orderedIds = a.take<uint32_t>(nn);
   s.tileSums = a.take<unsigned long long>((size_t)divUp(nn, PL_TILE) + 2);
+  s.state = a.take<PlocState>(PL_MAX_ITERS + 1);
   s.hostTotal = a.pinned;
-  if (!s.tileSums || !s.hostTotal) { err = "PLOC scratch does not fit the build arena"; return false; }
+  if (!s.tileSums || !s.state || !s.hostTotal) { err = "PLOC scratch does not fit the build arena"; return false; }
   return true;
 }
 
@@ -351,24 +379,34 @@ bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* p
   int cur = 0, count = n;
   uint32_t nodeBase = 0;
   unsigned long long* dTotal = s.tileSums + divUp((size_t)std::max(n, 2), PL_TILE);
-  int guard = 0;
+  PlocState* st = s.state;
+  PlocState* hostState = (PlocState*)s.hostTotal;   // 16 bytes of pinned memory
+  {
+    PlocState s0{n, 0u, 0u, 0u};
+    *hostState = s0;
+    PCK(cudaMemcpyAsync(st, hostState, sizeof s0, cudaMemcpyHostToDevice, stream));
+  }
+  int it = 0;
   while (count > PL_TAIL) {
-    int nTiles = divUp(count, PL_TILE);
-    k_ploc_nn<<<divUp(count, PL_THREADS), PL_THREADS, 0, stream>>>(count, radius, s.cLo[cur], s.cHi[cur], s.nn);
-    k_ploc_tile_sums<<<nTiles, PL_THREADS, 0, stream>>>(count, s.nn, s.tileSums);
-    k_ploc_scan_tiles<<<1, 1024, 0, stream>>>(nTiles, s.tileSums, dTotal);
-    k_ploc_merge<<<nTiles, PL_THREADS, 0, stream>>>(count, n, nodeBase, s.nn, s.tileSums, s.cid[cur], s.cLo[cur], s.cHi[cur],
-                                                     s.cid[cur ^ 1], s.cLo[cur ^ 1], s.cHi[cur ^ 1], s.nodeLo, s.nodeHi, s.children,
-                                                     s.parent, s.size);
-    PCK(cudaMemcpyAsync(s.hostTotal, dTotal, 8, cudaMemcpyDeviceToHost, stream));
+    if (it + PL_BATCH >= PL_MAX_ITERS) { err = "PLOC made no progress"; return false; }
+    // PL_BATCH iterations on the device's own counts; grids cover `count`, the last value the host has seen
+    const int nTiles = divUp(count, PL_TILE);
+    for (int b = 0; b < PL_BATCH; ++b, ++it) {
+      const int c = it & 1;
+      k_ploc_nn<<<divUp(count, PL_THREADS), PL_THREADS, 0, stream>>>(st + it, radius, s.cLo[c], s.cHi[c], s.nn);
+      k_ploc_tile_sums<<<nTiles, PL_THREADS, 0, stream>>>(st + it, s.nn, s.tileSums);
+      k_ploc_scan_tiles<<<1, 1024, 0, stream>>>(st + it, s.tileSums);
+      k_ploc_merge<<<nTiles, PL_THREADS, 0, stream>>>(st + it, n, s.nn, s.tileSums, s.cid[c], s.cLo[c], s.cHi[c],
+                                                       s.cid[c ^ 1], s.cLo[c ^ 1], s.cHi[c ^ 1], s.nodeLo, s.nodeHi, s.children,
+                                                       s.parent, s.size);
+    }
+    PCK(cudaMemcpyAsync(hostState, st + it, sizeof(PlocState), cudaMemcpyDeviceToHost, stream));
     PCK(cudaStreamSynchronize(stream));
-    unsigned long long total = *s.hostTotal;
-    int newCount = (int)(total & 0xffffffffull);
-    uint32_t merged = (uint32_t)(total >> 32);
-    if (merged == 0 || newCount != count - (int)merged || ++guard > 4096) { err = "PLOC made no progress"; return false; }
-    nodeBase += merged;
-    count = newCount;
-    cur ^= 1;
+    const PlocState got = *hostState;
+    if (got.count >= count || got.count < 1 || (int)got.nodeBase != n - got.count) { err = "PLOC made no progress"; return false; }
+    count = got.count;
+    nodeBase = got.nodeBase;
+    cur = (int)(got.iters & 1u);   // iterations that ran (the no-op ones at the end of a batch do not swap buffers)
   }
   if (count > 1) {
     uint32_t* dCreated = (uint32_t*)(dTotal + 1) + 1;

@@ -254,6 +254,10 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           if (COUNT) {
             atomicAdd((unsigned long long*)(job.counters + (ANYHIT ? 16 : 10)), (unsigned long long)nv);
             atomicAdd((unsigned long long*)(job.counters + (ANYHIT ? 18 : 12)), (unsigned long long)np);
+            if (ANYHIT) {   // words 20 / 21 (C_SH_BLOCKED / C_SH_TINTED): rays that touched their contribution record
+              if (atten.x == 0.f && atten.y == 0.f && atten.z == 0.f) atomicAdd(job.counters + 20, 1u);
+              else if (atten.x != 1.f || atten.y != 1.f || atten.z != 1.f) atomicAdd(job.counters + 21, 1u);
+            }
           }
           active = false;
         }

@@ -18,7 +18,7 @@ enum ShadeQueue { Q_LAMBERT = 0, Q_METAL = 1, Q_DIELECTRIC = 2, Q_DISNEY = 3, Q_
 enum CounterSlot { C_NEXT = 0, C_MAT0 = 1 /* ..4 */, C_SHQ = 5 /* shadow queue length */, C_BOUNCE_WORDS = 8,
                    C_NONFINITE = 8, C_SHADOW = 9, C_NODEVIS_LO = 10, C_NODEVIS_HI = 11,
                    C_PRIMTEST_LO = 12, C_PRIMTEST_HI = 13, C_CURSOR = 14, C_CURSOR_SHADOW = 15 /* the shadow launch may overlap the next extend launch */,
-                   C_NODEVIS_SH_LO = 16, C_PRIMTEST_SH_LO = 18, C_WORDS = 20 };
+                   C_NODEVIS_SH_LO = 16, C_PRIMTEST_SH_LO = 18, C_SH_BLOCKED = 20, C_SH_TINTED = 21, C_WORDS = 24 };
 constexpr int BOUNCE_RING = 4;   // per-bounce counter blocks kept alive at once
 
 struct PathBuffers {

@@ -73,10 +73,13 @@ class Stats(C.Structure):
                 ("prim_bytes", C.c_uint32), ("n_lights", C.c_uint32),
                 ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double),
                 ("ms_shadow", C.c_double), ("ms_accumulate", C.c_double), ("extend_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("node_visits_shadow", C.c_uint64), ("prim_tests_shadow", C.c_uint64), ("rays_shadow_traced", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("node_visits_shadow", C.c_uint64), ("prim_tests_shadow", C.c_uint64), ("rays_shadow_traced", C.c_uint64),
+                ("rays_shadow_blocked", C.c_uint64), ("rays_shadow_tinted", C.c_uint64),
+                ("rays_depth", C.c_uint64 * 8), ("shadow_traced_depth", C.c_uint64 * 8),
+                ("ms_extend_depth", C.c_double * 8), ("ms_shadow_depth", C.c_double * 8)]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if hasattr(getattr(self, k), "__len__") else getattr(self, k)) for k, _ in self._fields_}
 
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_GLASS, MAT_DISNEY, MAT_LIGHT = range(5)

@@ -41,7 +41,7 @@ def test_gpu_library_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), n
     lib.mox_abi_version.restype = C.c_int
-    assert lib.mox_abi_version() == 2
+    assert lib.mox_abi_version() == 3
 
 
 def test_gpu_library_fails_loudly_without_a_gpu():

@@ -123,7 +123,7 @@ def test_gpu_watertight_matches_oracle_bit_for_bit(orc, gpu_backend, flags):
     rays = np.concatenate([seam, rays_at_the_field(40000, 10)])
     to, io, bo, go = o.trace_closest(rays)
     tg, ig, bg, gg = g.trace_closest(rays)
-    assert (ig < 0).sum() == 0            # no leak on the GPU either (%d of the rays aim at seams)
+    assert len(seam) > 30000 and (ig < 0).sum() == 0     # no leak on the GPU either (the first len(seam) rays aim at seams)
     assert np.array_equal(io, ig)
     for a, b in ((to, tg), (bo, bg), (go, gg)):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
