@@ -61,6 +61,10 @@ class ClockSampler:
         self.reasons = set()
         self.max_mhz = None
         self.proc = None
+        self.marks = []
+
+    def mark(self):
+        self.marks.append(len(self.samples))
 
     def start(self):
         q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -96,8 +100,11 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        timed = self.samples[self.marks[0]:self.marks[1]] if len(self.marks) >= 2 else []
+        timed = timed or self.samples   # a timed region shorter than one sampling period: all samples under load
+        return {"sm_mhz": statistics.median(timed) if timed else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "samples_in_timed_region": len(timed),
+                "note": "nvidia-smi -lms 200 from before the warm-up to the end of the e2e run; sm_mhz = median inside the timed region"}
 
 
 def cpu_sample(args, steps, threads=0):
@@ -200,6 +207,11 @@ def main():
         return st["rays_primary"] + st["rays_bounce"]
 
     # ---- resident run: W warm-up steps, K timed steps + the gather
+    # the clock sampler starts before the warm-up: launching nvidia-smi takes driver locks for ~0.1 s, which must
+    # not fall into a timed region (it did: wall 123.7 ms/step against 111.3 on the device)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     gather()  # warm-up of the exchange too (communicator / peer-mapping set-up happens on the first call)
@@ -208,19 +220,22 @@ def main():
             tiles.read()
     barrier()
     s0 = ctx.stats()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
+    step_wall = []
     for _ in range(args.steps):
+        t_ = time.perf_counter()
         step()
+        step_wall.append(round((time.perf_counter() - t_) * 1e3, 2))
     g0.record()
     gather()
     g1.record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.mark()
     s1 = ctx.stats()
     dev_ms = (s1["ms_render"] - s0["ms_render"]) + g0.elapsed_time(g1)
     rays = rays_of(s1) - rays_of(s0)
@@ -256,7 +271,9 @@ def main():
     d2h = 0
     checksum = 0.0
     pending = False
+    e2e_step_wall = []
     for _ in range(args.steps):
+        t_ = time.perf_counter()
         ctx.set_camera(cam)
         step()
         gather()
@@ -267,12 +284,14 @@ def main():
                 checksum += float(img[::64, ::64].sum())  # touch the mapped result
             tiles.read_begin()
             pending = True
+        e2e_step_wall.append(round((time.perf_counter() - t_) * 1e3, 2))
     if rank == 0 and pending:
         img = tiles.read_end()
         d2h = img.nbytes
         checksum += float(img[::64, ::64].sum())
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
     e1 = ctx.stats()
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     ce = torch.tensor([rays_of(e1) - rays_of(e0)], dtype=torch.float64, device=dev)
@@ -391,7 +410,7 @@ def main():
                            "rng": "ref", "parallelism": f"tile-split x{world}, scene replicated, one gather per read-back",
                            "l2": "per-step path state (>0.7 GB) + scene exceed the 126 MB L2; no explicit flush"},
                 "spp_per_s": args.steps * SPP_PER_STEP / (dev_ms * 1e-3), "mshadow_per_s": shadow_all / (dev_ms * 1e3), "bvh_build_ms": build_ms,
-                "wall_ms_per_step": wall_ms / args.steps, "stage_ms": stage_ms,
+                "wall_ms_per_step": wall_ms / args.steps, "step_wall_ms": step_wall, "e2e_step_wall_ms": e2e_step_wall, "stage_ms": stage_ms,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 76 + 4, "d2h_bytes_per_step": int(d2h)},
                 "gather_bytes": tiles.bytes_on_the_wire(), "gather_transport": tiles.transport(), "gather_ms": g0.elapsed_time(g1), "render_ms_rank0": s1["ms_render"] - s0["ms_render"], "render_ms_per_rank": render_per_rank, "tile": TILE, "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline_shadow if (roofline_shadow and roofline and roofline_shadow["share_of_step"] > roofline["share_of_step"]) else roofline,
                 "roofline_closest": roofline, "roofline_shadow": roofline_shadow, "roofline_build": roofline_build,

@@ -111,26 +111,40 @@ __global__ void __launch_bounds__(TRAV_TPB, MOX_WIDE_MINBLOCKS) k_traverse_wide(
 
 // Bins the paths of the current queue by the shade class in their hit record.  A miss, a light and a path
 // beyond rayMaxDepth end here without a write: their last term is added by k_accumulate from the same record.
+// Queue slots are reserved once per block and class: a push per warp is a million atomics on one address per
+// launch at 4K x 4 spp, and same-address atomics retire about one per nanosecond — the kernel ran at 6-8 % issue
+// utilisation waiting for them (ncu, profiles/r2a_*).
 __global__ void __launch_bounds__(TPB) k_classify(LaunchCtx c, const uint32_t* __restrict__ queue, uint32_t count,
                                                   const uint32_t* __restrict__ countPtr, uint32_t depth) {
-  uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  __shared__ uint32_t sCount[TPB / 32][Q_COUNT];   // per warp and class: lanes that push
+  __shared__ uint32_t sBase[Q_COUNT];
+  const uint32_t i = blockIdx.x * TPB + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   if (countPtr) count = __ldg(countPtr);
-  if (i >= count) return;
-  uint32_t path = queue[i];
-  int bits = __float_as_int(c.pb.hit[path].y);
-  if (bits < 0) return;                                   // miss
-  uint32_t cls = (uint32_t)bits >> MOX_HIT_ID_BITS;
-  if (cls >= MOX_CLASS_LIGHT) return;                     // light(): terminal
-  const RenderParams& rp = c.rp;
-  // incoming payload colour is always (1,1,1): |colour| = sqrt(3)
-  if (depth > rp.maxDepth || length(mk3(1.f)) < rp.minIntensity) return;   // absorbed
-  // one warp-aggregated push per queue present in the warp (classes 0..3 are the queue indices)
-  for (uint32_t k = 0; k < Q_COUNT; ++k) {
-    if (cls == k) {
-      uint32_t pos = queuePush(c.bc + C_MAT0 + k);
-      c.pb.qMat[k][pos] = path;
-    }
+  uint32_t cls = Q_COUNT, path = 0;    // Q_COUNT: nothing to push
+  if (i < count) {
+    path = queue[i];
+    const int bits = __float_as_int(c.pb.hit[path].y);
+    const RenderParams& rp = c.rp;
+    // miss: bits < 0; light(): terminal; the incoming payload colour is always (1,1,1): |colour| = sqrt(3)
+    if (bits >= 0 && ((uint32_t)bits >> MOX_HIT_ID_BITS) < MOX_CLASS_LIGHT && !(depth > rp.maxDepth || length(mk3(1.f)) < rp.minIntensity))
+      cls = (uint32_t)bits >> MOX_HIT_ID_BITS;   // classes 0..3 are the queue indices
   }
+  uint32_t rankInWarp = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < Q_COUNT; ++k) {
+    const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+    if (lane == 0) sCount[warp][k] = (uint32_t)__popc(m);
+    if (cls == k) rankInWarp = (uint32_t)__popc(m & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  if (threadIdx.x < Q_COUNT) {
+    uint32_t total = 0;
+    for (int w = 0; w < TPB / 32; ++w) { const uint32_t n = sCount[w][threadIdx.x]; sCount[w][threadIdx.x] = total; total += n; }
+    sBase[threadIdx.x] = total ? atomicAdd(c.bc + C_MAT0 + threadIdx.x, total) : 0u;
+  }
+  __syncthreads();
+  if (cls < Q_COUNT) c.pb.qMat[cls][sBase[cls] + sCount[warp][cls] + rankInWarp] = path;
 }
 
 // ------------------------------------------------------------------ hit attributes (Geometry.cu)
@@ -249,15 +263,15 @@ __device__ __forceinline__ ShadeIn<RM> loadShadeIn(const LaunchCtx& c, uint32_t 
   return s;
 }
 
-__device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const float3& o, const float3& d, const float3& A,
-                                      int childState) {
+// Writes the spawned ray, the new throughput and RNG state, and queues the path at slot `pos` of the next queue.
+__device__ __forceinline__ void spawnAt(const LaunchCtx& c, uint32_t path, const float3& o, const float3& d, const float3& A,
+                                        int childState, uint32_t pos) {
   c.pb.rayO[path] = make_float4(o.x, o.y, o.z, c.rp.eps);
   c.pb.rayD[path] = make_float4(d.x, d.y, d.z, MOX_RAY_TMAX);
   float4 T = c.pb.thr[path];
   float3 t = mk3(T) * A;
   c.pb.thr[path] = make_float4(t.x, t.y, t.z, 0.f);
   c.pb.state[path] = childState;
-  uint32_t pos = queuePush(c.bc + C_NEXT);
   c.pb.qNext[pos] = path;
   if (c.pb.qKey) {
     // reordering key: 21-bit Morton cell of the origin (7 bits/axis of the scene box) | direction octant
@@ -269,6 +283,10 @@ __device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const f
     uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
     c.pb.qKey[pos] = (cell << 3) | oct;
   }
+}
+__device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const float3& o, const float3& d, const float3& A,
+                                      int childState) {
+  spawnAt(c, path, o, d, A, childState, queuePush(c.bc + C_NEXT));
 }
 
 // lambertian (Material.cu:28-43) and metal (:49-66)
@@ -322,11 +340,43 @@ constexpr int DISNEY_TPB = 128;
 #ifndef MOX_DISNEY_MINBLOCKS
 #define MOX_DISNEY_MINBLOCKS 6
 #endif
+
+// One reservation of `n` consecutive queue slots per thread with ONE atomic per block: warp scan, per-warp totals in
+// shared memory, thread 0 adds the block total to the counter.  Every thread of the block must call it.  Returns the
+// first slot of the calling thread.  (A push per warp and light is ~5 M atomics on two addresses per Disney launch
+// at 4K x 4 spp; same-address atomics retire about one per nanosecond.)
+__device__ __forceinline__ uint32_t blockReserve(uint32_t n, uint32_t* counter, uint32_t (&sWarp)[DISNEY_TPB / 32], uint32_t& sBase) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+#ifdef MOX_RESERVE_PER_WARP   // measured alternative: one atomic per warp
+  uint32_t wb = 0;
+  if (lane == 31u && incl) wb = atomicAdd(counter, incl);
+  return __shfl_sync(0xffffffffu, wb, 31) + incl - n;
+#endif
+  if (lane == 31u) sWarp[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < DISNEY_TPB / 32; ++w) { const uint32_t t = sWarp[w]; sWarp[w] = total; total += t; }
+    sBase = total ? atomicAdd(counter, total) : 0u;
+  }
+  __syncthreads();
+  const uint32_t first = sBase + sWarp[warp] + incl - n;
+  __syncthreads();   // the shared words are reused by the next reservation
+  return first;
+}
+
 template <int RM>
 __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
-  uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
-  if (i >= count) return;
-  ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DISNEY][i], depth);
+  __shared__ uint32_t sWarp[DISNEY_TPB / 32];
+  __shared__ uint32_t sBase;
+  const uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
+  const bool live = i < count;          // no early return: the block reserves its queue slots together
+  const uint32_t iq = live ? i : count - 1u;
+  ShadeIn<RM> s = loadShadeIn<RM>(c, c.pb.qMat[Q_DISNEY][iq], depth);
   Attr a = hitAttributes(c.scene, s.pd, s.o, s.d, s.t, true);
   const DisneyParams dp = s.m->dis;
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
@@ -338,48 +388,57 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   float3 L, H;
   const int nL = c.scene.nLights;
   uint32_t shadowCount = 0;
-  for (int li = 0; li < nL; ++li) {
-    const LightParams* lp = c.scene.lights + li;
-    float3 lpos = mk3(__ldg(&lp->position.x), __ldg(&lp->position.y), __ldg(&lp->position.z));
-    float3 pointOnLight, normalOnLight;
-    if (__ldg((const int*)&lp->shape) == SPHERE) {
-      pointOnLight = lpos + randInUnitSphere(s.rng) * __ldg(&lp->radius);
-      normalOnLight = normalize(pointOnLight - lpos);
-    } else {
-      float r1 = s.rng.rnd();
-      float r2 = s.rng.rnd();
-      pointOnLight = lpos + f3(lp->u) * r1 + f3(lp->v) * r2;
-      normalOnLight = mk3(__ldg(c.scene.lightN + li));
-    }
-    L = pointOnLight - a.front;
-    float lightDst = length(L);
-    L = normalize(L);
-    size_t slot = (size_t)li * count + i;  // light-major: neighbouring lanes aim at the same light
-    float3 contrib = mk3(0.f);
-    if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
-      shadowCount++;
-      H = normalize(L + V);
-      float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
-      float dr;
-      float objPdf = dh.pdf(L, H, dr);
-      if (lightPdf > 0 && objPdf > 0) {
-        float3 brdf = dh.eval(L, H, dr);
-        contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
+  for (int g0 = 0; g0 < nL; g0 += 32) {   // lights in groups of 32: one bit per light that needs a shadow ray
+    uint32_t traceMask = 0;
+    const int g1 = min(nL, g0 + 32);
+    for (int li = g0; li < g1; ++li) {
+      const LightParams* lp = c.scene.lights + li;
+      float3 lpos = mk3(__ldg(&lp->position.x), __ldg(&lp->position.y), __ldg(&lp->position.z));
+      float3 pointOnLight, normalOnLight;
+      if (__ldg((const int*)&lp->shape) == SPHERE) {
+        pointOnLight = lpos + randInUnitSphere(s.rng) * __ldg(&lp->radius);
+        normalOnLight = normalize(pointOnLight - lpos);
+      } else {
+        float r1 = s.rng.rnd();
+        float r2 = s.rng.rnd();
+        pointOnLight = lpos + f3(lp->u) * r1 + f3(lp->v) * r2;
+        normalOnLight = mk3(__ldg(c.scene.lightN + li));
+      }
+      L = pointOnLight - a.front;
+      float lightDst = length(L);
+      L = normalize(L);
+      size_t slot = (size_t)li * count + i;  // light-major: neighbouring lanes aim at the same light
+      float3 contrib = mk3(0.f);
+      if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
+        shadowCount++;
+        H = normalize(L + V);
+        float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
+        float dr;
+        float objPdf = dh.pdf(L, H, dr);
+        if (lightPdf > 0 && objPdf > 0) {
+          float3 brdf = dh.eval(L, H, dr);
+          contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
+        }
+      }
+      float3 pc = Tprev * contrib;
+      // a zero contribution needs no shadow ray (it is still counted, as the reference traces it)
+      if (live) {
+        c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
+        if (pc.x != 0.f || pc.y != 0.f || pc.z != 0.f) {
+          c.pb.shD[slot] = make_float4(L.x, L.y, L.z, lightDst - c.rp.eps);
+          traceMask |= 1u << (li - g0);
+        }
       }
     }
-    float3 pc = Tprev * contrib;
-    // a zero contribution needs no shadow ray (it is still counted, as the reference traces it)
-    bool trace = pc.x != 0.f || pc.y != 0.f || pc.z != 0.f;
-    c.pb.shC[slot] = make_float4(pc.x, pc.y, pc.z, 0.f);
-    if (trace) {
-      c.pb.shD[slot] = make_float4(L.x, L.y, L.z, lightDst - c.rp.eps);
-      uint32_t pos = queuePush(c.bc + C_SHQ);
-      c.pb.shQueue[pos] = (uint32_t)slot;
+    uint32_t pos = blockReserve((uint32_t)__popc(traceMask), c.bc + C_SHQ, sWarp, sBase);
+    while (traceMask) {
+      const int b = __ffs(traceMask) - 1;
+      traceMask &= traceMask - 1u;
+      c.pb.shQueue[pos++] = (uint32_t)((size_t)(g0 + b) * count + i);
     }
   }
-  if (nL) c.pb.shO[i] = make_float4(a.front.x, a.front.y, a.front.z, c.rp.eps);  // one origin for all lights of this hit
-  if (shadowCount) atomicAdd(c.pb.counters + C_SHADOW, shadowCount);
-  {  // + emission
+  if (nL && live) c.pb.shO[i] = make_float4(a.front.x, a.front.y, a.front.z, c.rp.eps);  // one origin for all lights of this hit
+  if (live) {  // + emission
     float3 e = f3(dp.emission);
     if (e.x != 0.f || e.y != 0.f || e.z != 0.f) {
       float3 r = mk3(c.pb.rad[s.path]) + Tprev * e;
@@ -388,17 +447,27 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   }
   disneySample(s.rng, dp, N, L, V, H);
   bool spawned = false;
-  if (dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
+  float3 A = mk3(0.f);
+  if (live && dot(N, L) > 0.0f && dot(N, V) > 0.0f) {
     float dr;
     float pdf = dh.pdf(L, H, dr);
     if (pdf > 0) {
       float3 brdf = dh.eval(L, H, dr);
-      spawn(c, s.path, a.front, L, brdf / pdf, s.rng.forkState((int)depth + 1));
+      A = brdf / pdf;
       spawned = true;
     }
   }
+  // shadow-ray statistics ride in the high half of the same reservation: one more atomic per block, not per warp
+  const uint32_t nextPos = blockReserve(spawned ? 1u : 0u, c.bc + C_NEXT, sWarp, sBase);
+  {
+    uint32_t sc = live ? shadowCount : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    if ((threadIdx.x & 31u) == 0u && sc) atomicAdd(c.pb.counters + C_SHADOW, sc);
+  }
+  if (spawned) spawnAt(c, s.path, a.front, L, A, s.rng.forkState((int)depth + 1), nextPos);
   // no indirect ray: the path ends with what it has; its (stale) hit record must not be read as a terminal hit
-  if (!spawned) c.pb.hit[s.path].y = __int_as_float(MOX_HIT_DEAD);
+  else if (live) c.pb.hit[s.path].y = __int_as_float(MOX_HIT_DEAD);
 }
 
 // The same program as two kernels.  k_shade_disney is 3 440 instructions at 80 registers (36 % occupancy, 12-15 % of
