@@ -10,8 +10,8 @@ materials and 4 quad lights at 3840x2160, max depth 5, rng=ref, fixed seed sched
 configuration the 1 Grays/s target is quoted on.  It fits one GPU, so N=1 runs exactly this; for
 N>1 the image is tile-split across ranks with the scene replicated (STRONG scaling: total work is
 fixed) and the accumulation buffer is gathered once at the end over NCCL.
-A step = SPP_PER_STEP (4) iterations of the reference's spp loop (MinimalOptiX.cpp:544-546), i.e.
-mox_render(ctx, 4, seed): +4 samples for every pixel; samples of one step may share a wavefront.
+A step = SPP_PER_STEP (8) iterations of the reference's spp loop (MinimalOptiX.cpp:544-546), i.e.
+mox_render(ctx, 8, seed): +8 samples for every pixel, rendered in wavefronts of at most 32 Mi paths.
 
   value   Mrays/s over the K timed steps, scene + BVH resident in HBM, device time = CUDA events on
           the launching stream (mox_stats.ms_render) + the gather, max over ranks.
@@ -32,7 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT, MAX_DEPTH, SEED = 3840, 2160, 5, 0xD1A1A6
-SPP_PER_STEP = 4  # one step = mox_render(4 spp): the spp loop of renderScene, 4 launches of the reference
+# One step = mox_render(8 spp): eight iterations of the spp loop of renderScene.  The library renders them in
+# wavefronts of at most 32 Mi paths: two of 4 spp on one GPU, one of 8 spp per GPU on eight (each GPU then owns an
+# eighth of the pixels) — the persistent traversal launches keep their length when the frame is split.
+SPP_PER_STEP = 8
 TRIS = 1_000_000
 WORKLOAD = f"interior ~1M-triangle Disney scene (BASELINE configs[3]), 3840x2160, {SPP_PER_STEP} spp per step, max depth 5, rng=ref"
 
@@ -53,7 +56,13 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe: clocks.sm, clocks.max.sm and
+    the clocks_event_reasons of `nvidia-smi --query-gpu ... -lms 200`).  Read through NVML in a thread of this process
+    — the same counters nvidia-smi prints — because an nvidia-smi child polling at 200 ms stalled this process's CUDA
+    calls by 40-60 ms per poll (measured: steps of 151-173 ms wall next to 107.6 ms ones, device time unchanged);
+    nvidia-smi is the fallback when the NVML binding is missing."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index = index
@@ -62,11 +71,29 @@ class ClockSampler:
         self.max_mhz = None
         self.proc = None
         self.marks = []
+        self.how = None
+        self.poll_ms = []
+        self._stop = threading.Event()
 
     def mark(self):
         self.marks.append(len(self.samples))
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES renumbers CUDA ordinals; NVML does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.how = "NVML (nvmlDeviceGetClockInfo / nvmlDeviceGetCurrentClocksEventReasons) every 200 ms"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -75,8 +102,27 @@ class ClockSampler:
         except OSError:
             self.proc = None
             return
+        self.how = "nvidia-smi -lms 200"
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
+
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            t0 = time.perf_counter()
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                try:
+                    bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except AttributeError:
+                    bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.poll_ms.append((time.perf_counter() - t0) * 1e3)
+            self._stop.wait(0.2)
 
     def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -94,6 +140,7 @@ class ClockSampler:
                     self.reasons.add(n)
 
     def stop(self):
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
             try:
@@ -104,7 +151,8 @@ class ClockSampler:
         timed = timed or self.samples   # a timed region shorter than one sampling period: all samples under load
         return {"sm_mhz": statistics.median(timed) if timed else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "samples_in_timed_region": len(timed),
-                "note": "nvidia-smi -lms 200 from before the warm-up to the end of the e2e run; sm_mhz = median inside the timed region"}
+                "how": self.how, "poll_ms_max": round(max(self.poll_ms), 2) if self.poll_ms else None,
+                "note": "sampled from before the warm-up to the end of the e2e run; sm_mhz = median inside the timed region"}
 
 
 def cpu_sample(args, steps, threads=0):
@@ -210,7 +258,7 @@ def main():
     # the clock sampler starts before the warm-up: launching nvidia-smi takes driver locks for ~0.1 s, which must
     # not fall into a timed region (it did: wall 123.7 ms/step against 111.3 on the device)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("MOX_BENCH_NO_SAMPLER") != "1":   # (the switch exists to measure the sampler's own cost)
         sampler.start()
     for _ in range(args.warmup):
         step()

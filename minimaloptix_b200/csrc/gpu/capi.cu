@@ -608,8 +608,21 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
 
 // Paths per batch: the configured cap, lowered so that the wavefront state fits into 60 % of the free device
 // memory for this scene's light count (36 bytes per path and light).
-size_t batchCap(mox_ctx* c) {
+size_t batchCap(mox_ctx* c, size_t wanted /* samples per pixel of this call */) {
   size_t cap = c->maxBatchPaths;
+  // The buffers of an earlier call already hold such a batch: nothing will be allocated, so there is nothing to
+  // budget.  (cudaMemGetInfo is a slow driver call — it was the 20-70 ms hiccup in front of some steps.)
+  if (c->nOwned) {
+    const size_t S = std::min(std::max<size_t>(1, cap / c->nOwned), wanted), nL = c->lights.size();   // samples per batch at the full cap
+    const int K = slicesFor(c, S * c->nOwned);
+    bool fits = true;
+    for (int k = 0; k < K && fits; ++k) {
+      const PathBuffers& pb = c->slices[k].pb;
+      const size_t nPix = (size_t)((uint64_t)c->nOwned * (k + 1) / K) - (size_t)((uint64_t)c->nOwned * k / K);   // as prepareBatch splits them
+      fits = pb.counters && pb.capacity >= S * nPix && pb.shadowSlots >= S * nPix * nL && pb.seedCap >= S;
+    }
+    if (fits) return cap;
+  }
   size_t freeB = 0, totalB = 0;
   if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
     size_t have = 0;
@@ -630,7 +643,7 @@ int renderSeeds(mox_ctx* c, const std::vector<int32_t>& seeds) {
   if ((rc = syncLights(c))) return rc;
   if ((rc = syncTextures(c))) return rc;
   if (c->nOwned == 0) { c->launches += seeds.size(); return MOX_OK; }
-  size_t perBatch = std::max<size_t>(1, batchCap(c) / c->nOwned);
+  size_t perBatch = std::max<size_t>(1, batchCap(c, seeds.size()) / c->nOwned);
   rc = prepareBatch(c, (uint32_t)std::min(perBatch, seeds.size()));
   if (rc && rc != MOX_ERR_OOM) return rc;   // out of memory: the loop below retries with smaller batches
   CUCK(c, cudaEventRecord(c->ev0, c->stream));
