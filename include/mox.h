@@ -223,6 +223,9 @@ int mox_get_stats(mox_ctx*, mox_stats*);
  * n_devices == 1 is allowed. */
 int mox_create_multi(mox_ctx** out, const int* device_ids, int n_devices);
 int mox_device_count(const mox_ctx*);   /* 1 for a plain context */
+/* mox_get_stats of device `index` (0 .. mox_device_count-1) of a multi-GPU handle alone — mox_get_stats on the handle
+ * sums the counts and takes the slowest device's times; per-device render times show the balance of the tile split. */
+int mox_get_device_stats(mox_ctx*, int index, mox_stats* out);
 
 /* Asynchronous accuBuffer->map(): _begin snapshots the accumulation buffer (for a multi-GPU
  * handle: gathers the tiles) and starts the device->host copy on a copy stream; rendering

@@ -48,6 +48,7 @@ SIGNATURES = {
     "unpack_owned": (C.c_int, [_vp, _u32, _vp]),
     "get_stats": (C.c_int, [_vp, C.POINTER(S.Stats)]),
     "device_count": (C.c_int, [_vp]),
+    "get_device_stats": (C.c_int, [_vp, C.c_int, C.POINTER(S.Stats)]),
     "read_accum_begin": (C.c_int, [_vp]),
     "read_accum_end": (C.c_int, [_vp, C.POINTER(_fp)]),
     "trace_closest": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
@@ -228,6 +229,11 @@ class Context:
 
     def device_count(self):
         return self.b.device_count(self.h)
+
+    def device_stats(self, index):
+        st = S.Stats()
+        self._ck(self.b.get_device_stats(self.h, index, C.byref(st)), "get_device_stats")
+        return st.asdict()
 
     # -- peer-memory tile gather across processes (one process per GPU)
     def gather_export(self, which):

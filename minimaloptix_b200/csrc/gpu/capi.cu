@@ -1374,6 +1374,12 @@ int mox_get_stats(mox_ctx* c, mox_stats* s) {
   return MOX_OK;
 }
 
+int mox_get_device_stats(mox_ctx* c, int index, mox_stats* s) {
+  if (!c) return MOX_ERR_INVALID;
+  if (index < 0 || index >= mox_device_count(c)) return fail(c, MOX_ERR_INVALID, "device index out of range");
+  return mox_get_stats(c->group ? groupChild(c->group, index) : c, s);
+}
+
 int mox_trace_closest_device(mox_ctx* c, const void* dev_rays, size_t n, void* dev_hits, float* out_ms) {
   if (!c) return MOX_ERR_INVALID;
   GROUP_FIRST(c, mox_trace_closest_device(k, dev_rays, n, dev_hits, out_ms));

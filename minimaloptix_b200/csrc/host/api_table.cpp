@@ -20,5 +20,7 @@ bool loadMoxApi(const char* libPath, const char* prefix, MoxApi& api, std::strin
   api.create_multi = (int (*)(mox_ctx**, const int*, int))dlsym(lib, (std::string(prefix) + "create_multi").c_str());
   api.read_accum_begin = (int (*)(mox_ctx*))dlsym(lib, (std::string(prefix) + "read_accum_begin").c_str());
   api.read_accum_end = (int (*)(mox_ctx*, const float**))dlsym(lib, (std::string(prefix) + "read_accum_end").c_str());
+  api.device_count = (int (*)(const mox_ctx*))dlsym(lib, (std::string(prefix) + "device_count").c_str());
+  api.get_device_stats = (int (*)(mox_ctx*, int, mox_stats*))dlsym(lib, (std::string(prefix) + "get_device_stats").c_str());
   return ok;
 }

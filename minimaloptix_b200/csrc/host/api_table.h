@@ -33,6 +33,8 @@ struct MoxApi {
   int (*create_multi)(mox_ctx**, const int*, int) = nullptr;
   int (*read_accum_begin)(mox_ctx*) = nullptr;
   int (*read_accum_end)(mox_ctx*, const float**) = nullptr;
+  int (*device_count)(const mox_ctx*) = nullptr;
+  int (*get_device_stats)(mox_ctx*, int, mox_stats*) = nullptr;
 };
 
 // prefix is "mox_" for the product library.  Returns false and fills err on failure.

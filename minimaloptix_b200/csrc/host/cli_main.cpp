@@ -88,10 +88,19 @@ int main(int argc, char** argv) {
 
   std::vector<float> accum((size_t)W * H * 3);
   std::vector<uint8_t> rgb((size_t)W * H * 3);
+  // a snapshot = updateContent (MinimalOptiX.cpp:556-560): map the accumulation buffer (on several GPUs: gather the
+  // tiles into device 0 over NVLink), quantise, write the image
+  double readSec = 0, writeSec = 0;
+  uint32_t nSnapshots = 0;
   auto save = [&](const std::string& name, uint32_t n) {
+    auto a0 = std::chrono::steady_clock::now();
     api.read_accum(ctx, accum.data());
+    auto a1 = std::chrono::steady_clock::now();
     moxh_accum_to_rgb8(accum.data(), W, H, (float)n, rgb.data());
     if (moxh_write_image((name + ".png").c_str(), rgb.data(), W, H)) fprintf(stderr, "write: %s\n", moxh_last_error());
+    readSec += std::chrono::duration<double>(a1 - a0).count();
+    writeSec += std::chrono::duration<double>(std::chrono::steady_clock::now() - a1).count();
+    nSnapshots++;
   };
   uint32_t done = 0, checkpoint = 1;
   if (!resume.empty()) {  // continue a previous run: same seed schedule, samples [launches, spp)
@@ -118,12 +127,20 @@ int main(int argc, char** argv) {
          "\"triangles\": %u, \"prims\": %u, \"bvh_build_ms\": %.3f, \"render_ms\": %.3f, \"wall_s\": %.3f, "
          "\"rays_primary\": %llu, \"rays_bounce\": %llu, \"rays_shadow\": %llu, \"mrays_per_s\": %.2f, \"mshadow_per_s\": %.2f, "
          "\"spp_per_s\": %.3f, \"nonfinite\": %llu, \"gpus\": %d, \"ms_extend\": %.2f, \"ms_shade\": %.2f, \"ms_shadow\": %.2f, "
-         "\"kernel_launches\": %llu}\n",
+         "\"kernel_launches\": %llu, \"snapshots\": %u, \"gather_and_readback_s\": %.4f, \"quantise_and_png_s\": %.3f, "
+         "\"render_ms_per_gpu\": [",
          scene.c_str(), W, H, spp, depth, seed, rng.c_str(), st.n_triangles, st.n_prims, buildMs, st.ms_render, sec,
          (unsigned long long)st.rays_primary, (unsigned long long)st.rays_bounce, (unsigned long long)st.rays_shadow,
          rays / (st.ms_render * 1e3), (double)st.rays_shadow / (st.ms_render * 1e3), spp / (st.ms_render * 1e-3),
          (unsigned long long)st.nonfinite_samples, gpus > 0 ? gpus : 1, st.ms_extend, st.ms_shade, st.ms_shadow,
-         (unsigned long long)st.kernel_launches);
+         (unsigned long long)st.kernel_launches, nSnapshots, readSec, writeSec);
+  const int nDev = api.device_count ? api.device_count(ctx) : 1;
+  for (int i = 0; i < nDev; ++i) {
+    mox_stats ds = st;
+    if (api.get_device_stats) api.get_device_stats(ctx, i, &ds);
+    printf("%s%.2f", i ? ", " : "", ds.ms_render);
+  }
+  printf("]}\n");
   api.destroy(ctx);
   return 0;
 }

@@ -835,6 +835,7 @@ int orc_read_accum(orc_ctx* c, float* dst) {
 int orc_map_accum(orc_ctx* c, const float** out) { if (!c || !out) return MOX_ERR_INVALID; *out = c->accu.data(); return MOX_OK; }
 int orc_unmap_accum(orc_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
 int orc_device_count(const orc_ctx* c) { return c ? 1 : 0; }
+int orc_get_device_stats(orc_ctx* c, int index, mox_stats* s) { return index == 0 ? orc_get_stats(c, s) : MOX_ERR_INVALID; }
 // host memory already: begin is a no-op, end hands out the accumulation buffer
 int orc_read_accum_begin(orc_ctx* c) { return c ? MOX_OK : MOX_ERR_INVALID; }
 int orc_read_accum_end(orc_ctx* c, const float** out) { return orc_map_accum(c, out); }

@@ -35,6 +35,7 @@ int orc_read_accum(orc_ctx*, float* dst_rgb);
 int orc_map_accum(orc_ctx*, const float** out);
 int orc_unmap_accum(orc_ctx*);
 int orc_device_count(const orc_ctx*);
+int orc_get_device_stats(orc_ctx*, int index, mox_stats* out);
 int orc_read_accum_begin(orc_ctx*);
 int orc_read_accum_end(orc_ctx*, const float** out);
 int orc_clear_accum(orc_ctx*);
