@@ -158,6 +158,7 @@ struct mox_ctx {
   size_t maxBatchPaths = 32u << 20;  // paths per wavefront (~280 B each with 4 lights); measured 4 Mi -> 947, 32 Mi -> 980 Mrays/s at 4K
   bool overlapShadow = true;     // shadow rays of bounce b on a second stream, concurrent with the extend launch of bounce b+1 (MOX_OVERLAP_SHADOW=0: serial)
   bool disneySplit = false;      // Disney NORMAL shading as two kernels sharing a per-hit record (MOX_DISNEY_SPLIT=0: one kernel)
+  bool brdfFast = true;          // approximate reciprocal / square root inside BRDF values (MOX_BRDF_IEEE=1: IEEE, the oracle's operations)
   bool hasDisneyNormal = false;  // some material runs the Disney NORMAL program (set by mox_build_accel)
   bool sortRays = false;         // reorder the extend queue by (origin cell, direction octant) from bounce 2 on
   float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {1, 1, 1};
@@ -320,6 +321,7 @@ SceneView sceneView(const mox_ctx* c) {
   s.textures = (const cudaTextureObject_t*)c->dTexObjs.p;
   s.nLights = (int)c->lights.size();
   s.nPrims = (int)c->prims.size();
+  s.nNodes8 = (uint32_t)c->nNodes8;
   s.watertight = (c->accelFlags & MOX_ACCEL_WATERTIGHT) ? 1 : 0;
   return s;
 }
@@ -555,6 +557,7 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     lc.accu = c->dAccu;
     lc.countTraversal = (c->accelFlags & MOX_ACCEL_COUNTERS) != 0;
     lc.disneySplit = c->disneySplit && pb.disneyRec != nullptr;
+    lc.brdfFast = c->brdfFast;
     lc.stream = sl.stream;
     lc.sceneLo = make_float3(c->sceneLo[0], c->sceneLo[1], c->sceneLo[2]);
     {
@@ -789,6 +792,7 @@ int mox_create(mox_ctx** out, int device_id) {
   if (const char* env = getenv("MOX_MAX_BATCH_PATHS")) { long long v = atoll(env); if (v > 0) c->maxBatchPaths = (size_t)v; }
   if (const char* env = getenv("MOX_DISNEY_SPLIT")) c->disneySplit = atoi(env) != 0;
   if (const char* env = getenv("MOX_OVERLAP_SHADOW")) c->overlapShadow = atoi(env) != 0;
+  if (const char* env = getenv("MOX_BRDF_IEEE")) c->brdfFast = atoi(env) == 0;
   if (const char* env = getenv("MOX_SLICES")) c->nSlices = std::min(std::max(atoi(env), 1), (int)mox_ctx::kMaxSlices);
   memset(&c->rp, 0, sizeof c->rp);
   c->rp.maxDepth = 256; c->rp.eps = 0.001f; c->rp.minIntensity = 0.001f;

@@ -116,6 +116,7 @@ struct SceneView {
   const cudaTextureObject_t* textures;  // id - 1 -> float4 texture, bilinear, REPEAT, normalized coords
   int nLights;
   int nPrims;
+  uint32_t nNodes8;         // nodes of the wide BVH
   int watertight;           // packed / packed8 triangle records hold raw vertices; the traversal runs the watertight test
 };
 

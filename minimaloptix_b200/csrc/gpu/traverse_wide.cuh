@@ -50,6 +50,17 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   const int lane = threadIdx.x & 31;
   const unsigned ltMask = (1u << lane) - 1u;
   const uint32_t jobCount = job.countPtr ? __ldg(job.countPtr) : job.count;
+#ifdef MOX_TOP_SMEM
+  // Measured option: the first MOX_TOP_SMEM nodes — the array is in level order, 73 = root + two
+  // levels — staged once per CTA in shared memory and read from there instead of through L1.
+  __shared__ float4 sTop[MOX_TOP_SMEM * 5];
+  {
+    const float4* src = (const float4*)s.nodes8;
+    const uint32_t nTop = min((uint32_t)MOX_TOP_SMEM, s.nNodes8) * 5u;
+    for (uint32_t k = threadIdx.x; k < nTop; k += blockDim.x) sTop[k] = __ldg(src + k);
+    __syncthreads();
+  }
+#endif
 #ifdef MOX_BYTE_PRMT
   // 0x3f800000 that ptxas cannot fold into an immediate (a launch never has 2^31 rays)
   const uint32_t one = 0x3f800000u | (job.count >> 31);
@@ -127,8 +138,19 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           const uint32_t nodeIdx = gBase + __popc(imaskG & ((1u << slot) - 1u));
           if (gBits & 0xff000000u) stack[sp++] = make_uint2(gBase, gBits);
           // ---- fetch and test the node
+#ifdef MOX_TOP_SMEM
+          float4 n0, n1, n2, n3, n4;
+          if (nodeIdx < (uint32_t)MOX_TOP_SMEM) {
+            const float4* t = sTop + nodeIdx * 5u;
+            n0 = t[0]; n1 = t[1]; n2 = t[2]; n3 = t[3]; n4 = t[4];
+          } else {
+            const BvhNode8* nd = s.nodes8 + nodeIdx;
+            n0 = __ldg(&nd->n0); n1 = __ldg(&nd->n1); n2 = __ldg(&nd->n2); n3 = __ldg(&nd->n3); n4 = __ldg(&nd->n4);
+          }
+#else
           const BvhNode8* nd = s.nodes8 + nodeIdx;
           const float4 n0 = __ldg(&nd->n0), n1 = __ldg(&nd->n1), n2 = __ldg(&nd->n2), n3 = __ldg(&nd->n3), n4 = __ldg(&nd->n4);
+#endif
           if (COUNT) nv++;
           const uint32_t ew = __float_as_uint(n0.w);
           const float iax = __uint_as_float((ew & 0xffu) << 23) * idir.x;

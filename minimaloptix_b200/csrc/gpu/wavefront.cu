@@ -350,7 +350,7 @@ __device__ __forceinline__ uint32_t blockReserve(uint32_t n, uint32_t* counter, 
   uint32_t incl = n;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
-#ifdef MOX_RESERVE_PER_WARP   // measured alternative: one atomic per warp
+#ifdef MOX_RESERVE_PER_WARP   // alternative for A/B runs: one atomic per warp
   uint32_t wb = 0;
   if (lane == 31u && incl) wb = atomicAdd(counter, incl);
   return __shfl_sync(0xffffffffu, wb, 31) + incl - n;
@@ -369,7 +369,7 @@ __device__ __forceinline__ uint32_t blockReserve(uint32_t n, uint32_t* counter, 
   return first;
 }
 
-template <int RM>
+template <int RM, bool F>
 __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disney(LaunchCtx c, uint32_t count, uint32_t depth) {
   __shared__ uint32_t sWarp[DISNEY_TPB / 32];
   __shared__ uint32_t sBase;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
   float3 baseColor = disneyBaseColor(c.scene, dp, a.u, a.v);
-  DisneyHit dh(dp, baseColor, N);
+  DisneyHit<F> dh(dp, baseColor, N);
   dh.setView(V);
   float3 Tprev = mk3(c.pb.thr[s.path]);
   float3 L, H;
@@ -412,12 +412,12 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
       if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
         shadowCount++;
         H = normalize(L + V);
-        float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
+        float lightPdf = bdiv<F>(bdiv<F>(lightDst * lightDst, __ldg(&lp->area)), dot(normalOnLight, -L));
         float dr;
         float objPdf = dh.pdf(L, H, dr);
         if (lightPdf > 0 && objPdf > 0) {
           float3 brdf = dh.eval(L, H, dr);
-          contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
+          contrib = powerHeuristic<F>(lightPdf, objPdf) * brdf * f3(lp->emission) * bdiv<F>(1.0f, fmaxf(0.001f, lightPdf));
         }
       }
       float3 pc = Tprev * contrib;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
     float pdf = dh.pdf(L, H, dr);
     if (pdf > 0) {
       float3 brdf = dh.eval(L, H, dr);
-      A = brdf / pdf;
+      A = brdf * bdiv<F>(1.0f, pdf);
       spawned = true;
     }
   }
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
 #ifndef MOX_DISNEY_NEE_MINBLOCKS
 #define MOX_DISNEY_NEE_MINBLOCKS 6
 #endif
-template <int RM>
+template <int RM, bool F>
 __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney_nee(LaunchCtx c, uint32_t count, uint32_t depth) {
   uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
   if (i >= count) return;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
   float3 N = faceforward3(a.Ns, -s.d, a.Ng);
   float3 V = -s.d;
   float3 baseColor = disneyBaseColor(c.scene, dp, a.u, a.v);
-  DisneyHit dh(dp, baseColor, N);
+  DisneyHit<F> dh(dp, baseColor, N);
   dh.setView(V);
   {  // what the BSDF-sampling kernel needs, word-major so that neighbouring hits store neighbouring words
     float4* rec = c.pb.disneyRec + i;
@@ -527,12 +527,12 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
     if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
       shadowCount++;
       H = normalize(L + V);
-      float lightPdf = lightDst * lightDst / __ldg(&lp->area) / dot(normalOnLight, -L);
+      float lightPdf = bdiv<F>(bdiv<F>(lightDst * lightDst, __ldg(&lp->area)), dot(normalOnLight, -L));
       float dr;
       float objPdf = dh.pdf(L, H, dr);
       if (lightPdf > 0 && objPdf > 0) {
         float3 brdf = dh.eval(L, H, dr);
-        contrib = powerHeuristic(lightPdf, objPdf) * brdf * f3(lp->emission) / fmaxf(0.001f, lightPdf);
+        contrib = powerHeuristic<F>(lightPdf, objPdf) * brdf * f3(lp->emission) * bdiv<F>(1.0f, fmaxf(0.001f, lightPdf));
       }
     }
     float3 pc = Tprev * contrib;
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
 #ifndef MOX_DISNEY_SAMPLE_MINBLOCKS
 #define MOX_DISNEY_SAMPLE_MINBLOCKS 8
 #endif
-template <int RM>
+template <int RM, bool F>
 __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_SAMPLE_MINBLOCKS) k_disney_sample(LaunchCtx c, uint32_t count, uint32_t depth) {
   uint32_t i = blockIdx.x * DISNEY_TPB + threadIdx.x;
   if (i >= count) return;
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_SAMPLE_MINBLOCKS) k_dis
   const float4* rec = c.pb.disneyRec + i;
   const size_t cap = c.pb.capacity;
   const float4 r0 = rec[0], r1 = rec[cap], r2 = rec[2 * cap], r3 = rec[3 * cap], r4 = rec[4 * cap], r5 = rec[5 * cap], r6 = rec[6 * cap];
-  DisneyHit dh(r0, r1, r2, r3, r4.w, r5, r6);
+  DisneyHit<F> dh(r0, r1, r2, r3, r4.w, r5, r6);
   const float3 N = dh.N, V = -mk3(c.pb.rayD[path]);
   dh.setView(V);
   RngT<RM> rng;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_SAMPLE_MINBLOCKS) k_dis
     float pdf = dh.pdf(L, H, dr);
     if (pdf > 0) {
       float3 brdf = dh.eval(L, H, dr);
-      spawn(c, path, mk3(r4), L, brdf / pdf, rng.forkState((int)depth + 1));
+      spawn(c, path, mk3(r4), L, brdf * bdiv<F>(1.0f, pdf), rng.forkState((int)depth + 1));
       spawned = true;
     }
   }
@@ -809,11 +809,14 @@ void launchShade(const LaunchCtx& c, int kind, uint32_t count, uint32_t depth) {
       break;
     case Q_DISNEY: {
       const unsigned g = (count + DISNEY_TPB - 1) / DISNEY_TPB;
-      if (c.disneySplit) {
-        if (ref) { k_disney_nee<0><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); k_disney_sample<0><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); }
-        else { k_disney_nee<1><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); k_disney_sample<1><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); }
-      } else if (ref) k_shade_disney<0><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
-      else k_shade_disney<1><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth);
+#define MOX_LAUNCH_DISNEY(RM, F)                                                                              \
+  do {                                                                                                        \
+    if (c.disneySplit) { k_disney_nee<RM, F><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); k_disney_sample<RM, F><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth); } \
+    else k_shade_disney<RM, F><<<g, DISNEY_TPB, 0, c.stream>>>(c, count, depth);                               \
+  } while (0)
+      if (ref) { if (c.brdfFast) MOX_LAUNCH_DISNEY(0, true); else MOX_LAUNCH_DISNEY(0, false); }
+      else { if (c.brdfFast) MOX_LAUNCH_DISNEY(1, true); else MOX_LAUNCH_DISNEY(1, false); }
+#undef MOX_LAUNCH_DISNEY
       break;
     }
   }

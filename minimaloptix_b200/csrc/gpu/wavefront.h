@@ -54,6 +54,7 @@ struct LaunchCtx {
   float* accu;               // device W*H*3
   bool countTraversal;
   bool disneySplit;          // Disney NORMAL as two kernels (light sampling, then BSDF sampling) instead of one
+  bool brdfFast;             // hardware reciprocal / square-root approximations inside BRDF values (shading.cuh::bdiv)
   float3 sceneLo, sceneInvExt;  // ray-reordering key: 7-bit cell of the origin inside the scene box
   cudaStream_t stream;
 };

@@ -279,6 +279,35 @@ def test_render_matches_oracle_ref_rng(host, api_tables, orc, gpu_backend, case)
     assert rel <= 1e-5
 
 
+@pytest.mark.parametrize("kind", ["cornell", "interior"])
+def test_brdf_ieee_mode_follows_the_oracle_operation_for_operation(host, api_tables, orc, gpu_backend, monkeypatch, kind):
+    """BRDF values use the hardware reciprocal / square-root approximations by default (shading.cuh::bdiv, ~2 ulp);
+    MOX_BRDF_IEEE=1 (read by mox_create) keeps every division and square root IEEE, i.e. the oracle's operations —
+    what is left then is libm (powf / logf / sinf / cosf).  Directions never use the approximations, so both modes
+    trace the same rays; the images of the two modes and the oracle agree far inside the 1e-5 the suite asserts."""
+    sc = host.Scene.load(os.path.join(ROOT, "scenes", "cornell"), "cornell") if kind == "cornell" else host.Scene.builtin("interior", 20000)
+    w, h, spp, seed = (128, 128, 16, 0xC0FFEE) if kind == "cornell" else (160, 90, 4, 0xD1A1A6)
+    o = orc.context()
+    sc.upload(api_tables.oracle, o, w, h, 5)
+    o.build_accel()
+    o.render(spp, seed)
+    ref, so = o.read_accum(), o.stats()
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MOX_BRDF_IEEE", mode)
+        g = gpu_backend.context(0)
+        sc.upload(api_tables.gpu, g, w, h, 5)
+        g.build_accel()
+        g.render(spp, seed)
+        st = g.stats()
+        res[mode] = (g.read_accum(), st["rays_bounce"], st["rays_shadow"], image_metrics(g.read_accum(), ref, spp))
+    print(kind, "ieee rmse/within/rel", res["1"][3], "fast", res["0"][3], "fast vs ieee", image_metrics(res["0"][0], res["1"][0], spp))
+    assert res["1"][1:3] == res["0"][1:3]                          # the same rays in both modes
+    assert abs(res["1"][1] - so["rays_bounce"]) <= 1e-5 * so["rays_bounce"] + 1
+    assert res["1"][3][0] <= 2e-6 and res["0"][3][0] <= 1e-5        # RMSE against the oracle
+    assert image_metrics(res["0"][0], res["1"][0], spp)[0] <= 2e-6  # the approximations themselves
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "scenes", "coffee", "coffee.scene")), reason="scenes/coffee not fetched")
 def test_render_coffee_matches_oracle(host, api_tables, orc, gpu_backend):
     """BASELINE config 3 at reduced size.  The coffee materials have roughness 0.001-0.01: GTR2 is
