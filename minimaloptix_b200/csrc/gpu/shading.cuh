@@ -41,6 +41,8 @@ MOX_D float sqr(float x) { return x * x; }
 // Default F = true (shade stage 49.1 -> 41.8 ms per step, images within 1e-5 RMSE of the oracle as before);
 // MOX_BRDF_IEEE=1 selects F = false, whose values follow the oracle's operations one for one.
 template <bool F> MOX_D float bdiv(float a, float b) { return F ? __fdividef(a, b) : a / b; }
+template <bool F> MOX_D float bpow(float x, float y) { return F ? __powf(x, y) : powf(x, y); }   // ex2(y * lg2(x)): NaN for x < 0 like powf
+template <bool F> MOX_D float blog(float x) { return F ? __logf(x) : logf(x); }
 template <bool F> MOX_D float bsqrt(float x) {
   if (!F) return sqrtf(x);
   float r;
@@ -131,7 +133,7 @@ struct DisneyHit {
   MOX_D DisneyHit(const DisneyParams& mp, const float3& baseColor, const float3& n) {
     N = n;
     Onb3 onb(N);
-    Cdlin = mk3(powf(baseColor.x, 2.2f), powf(baseColor.y, 2.2f), powf(baseColor.z, 2.2f));
+    Cdlin = mk3(bpow<F>(baseColor.x, 2.2f), bpow<F>(baseColor.y, 2.2f), bpow<F>(baseColor.z, 2.2f));
     float Cdlum = dot(Cdlin, mk3(0.3f, 0.6f, 0.1f));
     float3 Ctint = Cdlum > 0.f ? Cdlin / Cdlum : mk3(1.f);
     Cspec0 = lerp3(mp.specular * 0.08f * lerp3(mk3(1.f), Ctint, mp.specularTint), Cdlin, mp.metallic);
@@ -163,7 +165,7 @@ struct DisneyHit {
     specularRatio = 1.f - diffuseRatio;
     float a2 = clearcoatAlpha * clearcoatAlpha;
     ccA2m1 = a2 - 1.0f;
-    ccPiLog = MOX_PI_F * logf(a2);
+    ccPiLog = MOX_PI_F * blog<F>(a2);
     piAxAy = MOX_PI_F * ax * ay;
     quarterClearcoat = 0.25f * clearcoat;
     oneMinusMetallic = 1.0f - metallic;
