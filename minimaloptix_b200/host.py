@@ -134,7 +134,10 @@ class Scene:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().moxh_scene_free(self.h)
+            try:
+                lib().moxh_scene_free(self.h)
+            except TypeError:   # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
     def info(self):

@@ -91,6 +91,35 @@ def soup_case(n_tris, out):
         res["sweep"].append({"rays": n, "ms_ploc": ms, "mrays_per_s_ploc": n / ms / 1e3, "ms_lbvh": ms_l,
                              "mrays_per_s_lbvh": n / ms_l / 1e3, "hit_fraction": hit_frac})
         del o, d, r, hits
+    # roofline of the incoherent-ray batch: n-bar from a counting build of the same kernel on 2^24 rays
+    gc = mox.gpu().context(0)
+    sc.upload(GPU, gc, 64, 64, 5)
+    gc.build_accel(mox.structs.ACCEL_COUNTERS)
+    n = 1 << 24
+    o = torch.rand((n, 3), generator=gen, device="cuda")
+    d = torch.randn((n, 3), generator=gen, device="cuda")
+    d = d / d.norm(dim=1, keepdim=True)
+    r = torch.empty((n, 8), device="cuda")
+    r[:, 0:3] = o; r[:, 3] = 1e-3; r[:, 4:7] = d; r[:, 7] = 1e27
+    hits = torch.empty((n, 4), device="cuda")
+    torch.cuda.synchronize()
+    gc.trace_closest_device(r.data_ptr(), n, hits.data_ptr())
+    cs = gc.stats()
+    ms = min(g.trace_closest_device(r.data_ptr(), n, hits.data_ptr()) for _ in range(3))
+    nn, npr = cs["node_visits"] / n, cs["prim_tests"] / n
+    b_ray = 48 + nn * cs["node_bytes"] + npr * cs["prim_bytes"]
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    ach = n * b_ray / (ms * 1e-3) / 1e9
+    res["roofline"] = {"bound": "hbm", "kernel": "k_traverse_wide<closest> (raw query, 2^24 incoherent rays)", "rays": n, "ms": ms,
+                       "mrays_per_s": n / ms / 1e3, "nodes_per_ray": nn, "prims_per_ray": npr, "node_bytes": cs["node_bytes"],
+                       "prim_bytes": cs["prim_bytes"], "bytes_per_ray": b_ray, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                       "scene_bytes": cs["n_nodes"] * cs["node_bytes"] + n_tris * cs["prim_bytes"]}
+    res["roofline_build"] = {"bytes_per_triangle": 450, "ms": min(builds), "achieved": 450.0 * n_tris / (min(builds) * 1e-3) / 1e9,
+                             "frac": 450.0 * n_tris / (min(builds) * 1e-3) / 1e9 / peak, "ms_lbvh": min(lbvh),
+                             "frac_lbvh": 450.0 * n_tris / (min(lbvh) * 1e-3) / 1e9 / peak}
     print(json.dumps(res), flush=True)
     out.append(res)
 
