@@ -432,6 +432,45 @@ def test_zoo_every_program_matches_oracle(host, orc, gpu_backend, mode, textured
     assert np.any(ob.trace_shadow(rays) != g.trace_shadow(rays), axis=1).sum() <= 2
 
 
+def test_disney_with_more_than_32_lights(host, orc, gpu_backend):
+    """The Disney kernel reserves its shadow-queue slots once per group of 32 lights (one bit per light): 40 quad lights
+    and one sphere light cross the group boundary.  Equal ray counts — one shadow ray per light and hit that faces it —
+    and the image of the oracle."""
+    d = S.DisneyParams()
+    d.color = S.float3(0.7, 0.6, 0.5); d.specular = d.roughness = d.sheenTint = 0.5; d.clearcoatGloss = 1.0; d.metallic = 0.2
+    floor = S.DisneyParams()
+    floor.color = S.float3(0.4, 0.5, 0.6); floor.specular = floor.roughness = floor.sheenTint = 0.5; floor.clearcoatGloss = 1.0
+    lights = []
+    for k in range(40):
+        lq = S.LightParams()
+        x, z = -3.0 + 0.75 * (k % 8), -2.0 + 0.9 * (k // 8)
+        lq.position, lq.u, lq.v, lq.normal = S.float3(x, 3.0, z), S.float3(0.3, 0, 0), S.float3(0, 0, 0.3), S.float3(0, -1, 0)
+        lq.area, lq.emission, lq.shape = 0.09, S.float3(3, 3, 3), S.QUAD
+        lights.append(lq)
+    ls = S.LightParams()
+    ls.position, ls.radius, ls.area, ls.emission, ls.shape = S.float3(2.5, 1.0, 1.5), 0.2, 4 * 3.14159265 * 0.04, S.float3(6, 5, 4), S.SPHERE
+    lights.append(ls)
+    out = []
+    for ctx in (orc.context(), gpu_backend.context(0)):
+        ctx.set_globals(96, 64, 4, bg=(0.05, 0.05, 0.05))
+        ctx.set_camera(host.set_cam_params((0, 1.5, 5), (0, 0.5, 0), (0, 1, 0), 40, 1.5, 0.0, 1.0))
+        ctx.add_sphere(S.SphereParams(0.8, S.float3(0, 0.8, 0), S.float3()), S.MAT_DISNEY, d)
+        ctx.add_quad(host.set_quad_params((-6, 0, -6), (12, 0, 0), (0, 0, 12)), S.MAT_DISNEY, floor)
+        for lq in lights[:40]:
+            ctx.add_quad(host.set_quad_params((lq.position.x, lq.position.y, lq.position.z), (0.3, 0, 0), (0, 0, 0.3)), S.MAT_LIGHT, lq)
+        ctx.add_sphere(S.SphereParams(0.2, S.float3(2.5, 1.0, 1.5), S.float3()), S.MAT_LIGHT, ls)
+        ctx.set_lights(lights)
+        ctx.build_accel()
+        ctx.render(3, 41)
+        st = ctx.stats()
+        out.append((ctx.read_accum(), st["rays_bounce"], st["rays_shadow"], st["nonfinite_samples"]))
+    assert out[0][1:] == out[1][1:]
+    assert out[1][2] > 41 * 1000
+    rmse, within, rel = image_metrics(out[1][0], out[0][0], 3)
+    print("41 lights: rmse", rmse, "shadow rays", out[1][2])
+    assert rmse <= 1e-5 and within >= 0.9999
+
+
 def test_nonfinite_samples_become_bad_color(host, orc, gpu_backend):
     """Exception.cu:10-12 / MinimalOptiX.cpp:149-151: badColor is what the reference paints when a launch index
     fails.  Here a NaN/Inf sample is that failure: a Disney material with a negative colour (pow(c, 2.2) = NaN) and a NaN emission.
