@@ -103,14 +103,35 @@ MOX_D bool quadTest(const Analytic& q, const float3& o, const float3& d, float t
 
 struct RayPre { float3 o, d, idir; float tmin; };
 
+// 1/d feeds the box slabs only, which are conservative by more than its error (far side x 1.00001, near/far
+// addends moved by 2^-21 of the origin term): the hardware reciprocal (1 ulp) instead of the IEEE sequence and its
+// slow-path branch, three times per ray.  Primitive tests never see it.
+MOX_D float slabRcp(float x) {
+#ifdef MOX_IDIR_IEEE
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
 MOX_D RayPre prepRay(const float3& o, const float3& d, float tmin) {
   RayPre r;
   r.o = o; r.d = d; r.tmin = tmin;
   const float tiny = 1e-30f;
-  r.idir.x = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-  r.idir.y = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-  r.idir.z = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+  r.idir.x = slabRcp(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+  r.idir.y = slabRcp(fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+  r.idir.z = slabRcp(fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
   return r;
+}
+
+// Shadow rays of one hit share their origin: ray id = light * hits + hit, origin = rayO[id % hits].  The quotient is
+// at most the number of lights, so one multiply-high by floor(2^32 / hits) + 1 gives it or one more.
+MOX_D uint32_t originIndex(const TraceJob& job, uint32_t id) {
+  if (job.originMod <= 1u) return job.originMod ? 0u : id;   // (the magic of 1 does not fit 32 bits)
+  const uint32_t q = __umulhi(id, job.originMagic);
+  const uint32_t r = id - q * job.originMod;
+  return (int32_t)r < 0 ? r + job.originMod : r;
 }
 
 // Entry distance of the slab test, or +inf when the box is missed within [tmin, tcur].
@@ -190,7 +211,7 @@ __device__ __forceinline__ void traverseWarpPersistent(const SceneView& s, const
           uint32_t i = base + __popc(idle & ltMask);
           if (i < jobCount) {
             rayId = job.queue ? MOX_LD_STREAM(job.queue + i) : i;
-            uint32_t oId = job.originMod ? rayId % job.originMod : rayId;
+            const uint32_t oId = originIndex(job, rayId);
             float4 ro = MOX_LD_STREAM(job.rayO + oId), rd = MOX_LD_STREAM(job.rayD + rayId);
             if (!(ANYHIT && rd.w < 0.f)) {
               r = prepRay(mk3(ro), mk3(rd), ro.w);

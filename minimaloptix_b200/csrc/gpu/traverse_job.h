@@ -17,6 +17,7 @@ struct TraceJob {
   uint32_t count;
   const uint32_t* countPtr;  // when set, the ray count is read from device memory instead
   uint32_t originMod;        // when non-zero, the origin of ray id is rayO[id % originMod]
+  uint32_t originMagic;      // floor(2^32 / originMod) + 1: id / originMod = umulhi(id, magic) or one less (set by launchTraverse)
   uint32_t* cursor;
   float4* hits;
   float2* hits2;

@@ -93,7 +93,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           uint32_t i = base + __popc(idle & ltMask);
           if (i < jobCount) {
             rayId = job.queue ? MOX_LD_STREAM(job.queue + i) : i;
-            uint32_t oId = job.originMod ? rayId % job.originMod : rayId;
+            const uint32_t oId = originIndex(job, rayId);
             float4 ro = MOX_LD_STREAM(job.rayO + oId), rd = MOX_LD_STREAM(job.rayD + rayId);
             if (!(ANYHIT && rd.w < 0.f)) {
               RayPre r = prepRay(mk3(ro), mk3(rd), ro.w);

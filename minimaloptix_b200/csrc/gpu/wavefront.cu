@@ -772,6 +772,7 @@ void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool
   if (!jobIn.count) return;
   TraceJob job = jobIn;
   job.fetchThreshold = fetchThreshold(anyHit);
+  job.originMagic = job.originMod ? (uint32_t)(0x100000000ull / job.originMod) + 1u : 0u;
   cudaMemsetAsync(job.cursor, 0, 4, stream);
   if (anyHit && count) launchTraverseT<true, true, false>(s, job, stream);
   else if (anyHit) launchTraverseT<true, false, false>(s, job, stream);
