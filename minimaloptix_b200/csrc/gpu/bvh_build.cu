@@ -386,6 +386,17 @@ __global__ void k_pack(int n, const uint32_t* __restrict__ sortedIds, const Prim
 
 inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
+// Grid of the grid-stride histogram kernel: eight 256-thread blocks per SM of the current device.
+inline int histGridCap() {
+  static const int cap = [] {   // thread-safe one-time initialisation (a multi-GPU handle builds from several host threads)
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (sms > 0 ? sms : 148) * 8;
+  }();
+  return cap;
+}
+
 }  // namespace
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
@@ -487,7 +498,7 @@ bool buildBvh(const BuildInput& in, BuildOutput& out, cudaStream_t stream, std::
   const int B = 256;
   k_prim_bounds<<<divUp(n, B), B, 0, stream>>>(n, in.prims, in.tris, in.verts, in.analytic, boxLo, boxHi, small, small + 6);
   k_morton<<<divUp(n, B), B, 0, stream>>>(n, boxLo, boxHi, small, keysA, valsA);
-  k_sort_hist<<<std::min(divUp(n, B * 8), 148 * 8), B, 0, stream>>>(keysA, n, small + 16);
+  k_sort_hist<<<std::min(divUp(n, B * 8), histGridCap()), B, 0, stream>>>(keysA, n, small + 16);
   k_sort_scan_hist<<<1, 256, 0, stream>>>(small + 16);
   uint32_t *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
   for (int p = 0; p < 4; ++p) {
@@ -579,7 +590,7 @@ bool radixSortPairs(uint32_t* keys, uint32_t* vals, int n, cudaStream_t stream, 
   CK(cudaMalloc(&small, (16 + 1024) * 4)); CK(cudaMalloc(&status, (size_t)4 * nTiles * 256 * 4));
   CK(cudaMemsetAsync(small, 0, (16 + 1024) * 4, stream));
   CK(cudaMemsetAsync(status, 0, (size_t)4 * nTiles * 256 * 4, stream));
-  k_sort_hist<<<std::min(divUp(n, 256 * 8), 148 * 8), 256, 0, stream>>>(keys, n, small + 16);
+  k_sort_hist<<<std::min(divUp(n, 256 * 8), histGridCap()), 256, 0, stream>>>(keys, n, small + 16);
   k_sort_scan_hist<<<1, 256, 0, stream>>>(small + 16);
   uint32_t *kin = keys, *vin = vals, *kout = keysB, *vout = valsB;
   for (int p = 0; p < 4; ++p) {
@@ -610,7 +621,7 @@ void radixSortAsync(uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t*
   uint32_t* small = scratch;
   uint32_t* status = scratch + 16 + 1024;
   cudaMemsetAsync(scratch, 0, ((size_t)(16 + 1024) + (size_t)passes * nTiles * 256) * 4, stream);
-  k_sort_hist<<<std::min(divUp(n, 256 * 8), 148 * 8), 256, 0, stream>>>(keysA, n, small + 16);
+  k_sort_hist<<<std::min(divUp(n, 256 * 8), histGridCap()), 256, 0, stream>>>(keysA, n, small + 16);
   k_sort_scan_hist<<<1, 256, 0, stream>>>(small + 16);
   uint32_t *kin = keysA, *vin = valsA, *kout = keysB, *vout = valsB;
   for (int p = 0; p < passes; ++p) {

@@ -84,6 +84,7 @@ struct mox_ctx {
   DevBuf dPrims, dTris, dVerts, dNormals, dUvs, dAnalytic, dMats, dLights, dLightN, dShadeRec;
   bool shadeRecBuilt = false;
   DevBuf dQueryO, dQueryD, dQueryCounters;  // raw ray queries
+  DevBuf dQueryRays, dQueryOut, dQueryC;    // ... and their host-buffer forms: grow-only staging, no allocation per call
   DevBuf dTexObjs;
   BvhNode2* dNodes = nullptr;
   float4* dPacked = nullptr;
@@ -806,7 +807,7 @@ void mox_destroy(mox_ctx* c) {
   if (c->group) { groupDestroy(c->group); delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dLightN, &c->dShadeRec, &c->dQueryO,
+  for (DevBuf* b : {&c->dPrims, &c->dTris, &c->dVerts, &c->dNormals, &c->dUvs, &c->dAnalytic, &c->dMats, &c->dLights, &c->dLightN, &c->dShadeRec, &c->dQueryRays, &c->dQueryOut, &c->dQueryC, &c->dQueryO,
                    &c->dQueryD, &c->dQueryCounters}) b->release();
   for (auto& b : c->otherOwned) b.release();
   freeTextures(c);
@@ -1430,19 +1431,13 @@ int mox_trace_closest(mox_ctx* c, const float* rays, size_t n, void* hits) {
   if (!n) return MOX_OK;
   int rc = bind(c);
   if (rc) return rc;
-  void *dRays = nullptr, *dHits = nullptr;
-  CUCK(c, cudaMalloc(&dRays, n * 32));
-  CUCK(c, cudaMalloc(&dHits, n * 16));
+  if ((rc = ensure(c, c->dQueryRays, n * 32)) || (rc = ensure(c, c->dQueryOut, n * 16))) return rc;
+  void *dRays = c->dQueryRays.p, *dHits = c->dQueryOut.p;
   // stream-ordered: the traversal kernel runs on the (non-blocking) context stream
-  { cudaError_t e = cudaMemcpyAsync(dRays, rays, n * 32, cudaMemcpyHostToDevice, c->stream);
-    if (e != cudaSuccess) { cudaFree(dRays); cudaFree(dHits); return fail(c, MOX_ERR_CUDA, cudaGetErrorString(e)); } }
-  rc = mox_trace_closest_device(c, dRays, n, dHits, nullptr);
-  if (!rc) {
-    cudaError_t e = cudaMemcpy(hits, dHits, n * 16, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = fail(c, MOX_ERR_CUDA, cudaGetErrorString(e));
-  }
-  cudaFree(dRays); cudaFree(dHits);
-  return rc;
+  CUCK(c, cudaMemcpyAsync(dRays, rays, n * 32, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = mox_trace_closest_device(c, dRays, n, dHits, nullptr))) return rc;
+  CUCK(c, cudaMemcpy(hits, dHits, n * 16, cudaMemcpyDeviceToHost));
+  return MOX_OK;
 }
 
 int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
@@ -1454,14 +1449,10 @@ int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
   if (!n) return MOX_OK;
   int rc = bind(c);
   if (rc) return rc;
-  void *dRays = nullptr, *dOut = nullptr, *dC = nullptr;
-  CUCK(c, cudaMalloc(&dRays, n * 32));
-  CUCK(c, cudaMalloc(&dOut, n * 12));
-  CUCK(c, cudaMalloc(&dC, n * 16));
-  if ((rc = ensure(c, c->dQueryO, n * 16)) || (rc = ensure(c, c->dQueryD, n * 16)) || (rc = ensure(c, c->dQueryCounters, C_WORDS * 4))) {
-    cudaFree(dRays); cudaFree(dOut); cudaFree(dC);
+  if ((rc = ensure(c, c->dQueryRays, n * 32)) || (rc = ensure(c, c->dQueryOut, n * 16)) || (rc = ensure(c, c->dQueryC, n * 16)) ||
+      (rc = ensure(c, c->dQueryO, n * 16)) || (rc = ensure(c, c->dQueryD, n * 16)) || (rc = ensure(c, c->dQueryCounters, C_WORDS * 4)))
     return rc;
-  }
+  void *dRays = c->dQueryRays.p, *dOut = c->dQueryOut.p, *dC = c->dQueryC.p;
   uint32_t* counters = (uint32_t*)c->dQueryCounters.p;
   cudaMemcpyAsync(dRays, rays, n * 32, cudaMemcpyHostToDevice, c->stream);   // stream-ordered, see mox_trace_closest
   cudaMemsetAsync(counters, 0, C_WORDS * 4, c->stream);
@@ -1475,7 +1466,6 @@ int mox_trace_shadow(mox_ctx* c, const float* rays, size_t n, float* out_rgb) {
   cudaError_t e = cudaStreamSynchronize(c->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out_rgb, dOut, n * 12, cudaMemcpyDeviceToHost);
-  cudaFree(dRays); cudaFree(dOut); cudaFree(dC);
   if (e != cudaSuccess) return fail(c, MOX_ERR_CUDA, cudaGetErrorString(e));
   return MOX_OK;
 }
