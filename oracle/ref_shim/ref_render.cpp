@@ -493,6 +493,7 @@ int ref_get_stats(ref_ctx* c, mox_stats* s) {
   s->n_triangles = s->n_prims - s->n_spheres - s->n_quads; s->n_lights = (uint32_t)c->lights.size();
   return MOX_OK;
 }
+int ref_get_device_stats(ref_ctx* c, int index, mox_stats* s) { return index == 0 ? ref_get_stats(c, s) : MOX_ERR_INVALID; }
 // Exception.cu:10-12 for one pixel.
 int ref_exception(ref_ctx* c, uint32_t x, uint32_t y) {
   if (!c || x >= c->W || y >= c->H) return MOX_ERR_INVALID;
