@@ -56,6 +56,7 @@ struct PlocScratch {
   float4 *nodeLo = nullptr, *nodeHi = nullptr;
   uint2* children = nullptr;
   uint32_t *parent = nullptr, *size = nullptr, *leafPos = nullptr, *orderedIds = nullptr;
+  uint32_t* firstPos = nullptr;   // per inner node (id - nLeaves): leaf-order position of its leftmost leaf
   unsigned long long* tileSums = nullptr;
   PlocState* state = nullptr;               // loop state, one slot per iteration (ploc.cu)
   unsigned long long* hostTotal = nullptr;  // pinned

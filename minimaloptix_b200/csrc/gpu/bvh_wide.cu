@@ -111,7 +111,7 @@ __global__ void k_collapse_dp(int nLeaves, uint32_t root, const uint2* __restric
 __global__ void __launch_bounds__(128)
 k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, const uint2* __restrict__ children,
                  const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi, const uint32_t* __restrict__ size,
-                 const uint32_t* __restrict__ parent, const uint32_t* __restrict__ leafPos, uint32_t root,
+                 const uint32_t* __restrict__ parent, const uint32_t* __restrict__ leafPos, const uint32_t* __restrict__ firstPos, uint32_t root,
                  const uint32_t* __restrict__ orderedIds, BvhNode8* __restrict__ out, uint32_t* __restrict__ orderedIds8,
                  WorkItem* __restrict__ nextItems, uint32_t* __restrict__ counters /* [0] nodes, [1] prims */,
                  const uint32_t* __restrict__ levelCount /* items of this level; [1]: of the next, filled here */,
@@ -244,11 +244,7 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
       // first primitive of the subtree in binary leaf order
       uint32_t first;
       if (c < (uint32_t)nLeaves) first = leafPos[c];
-      else {
-        uint32_t node = c, pos = 0;
-        while (node != root) { uint32_t p = parent[node]; uint2 pc = children[p - nLeaves]; if (pc.y == node) pos += size[pc.x]; node = p; }
-        first = pos;
-      }
+      else first = firstPos[c - nLeaves];   // leaf-order position of the subtree's first primitive (k_ploc_leaf_order)
       for (uint32_t k = 0; k < cnt; ++k) orderedIds8[primBase + primOff + k] = orderedIds[first + k];
       meta[s] = (((1u << cnt) - 1u) << 5) | primOff;
       primOff += cnt;
@@ -316,7 +312,7 @@ bool wideCollapse(const PlocScratch& s, int n, uint32_t root, DeviceArena& arena
   for (bool more = true; more;) {
     if (levels + kLevelBatch >= kMaxLevels) { err = "wide collapse did not terminate"; return false; }
     for (int b = 0; b < kLevelBatch; ++b, ++levels) {
-      k_collapse_level<<<divUp(bound, 128), 128, 0, stream>>>((int)bound, q[cur], n, s.children, s.nodeLo, s.nodeHi, s.size, s.parent, s.leafPos,
+      k_collapse_level<<<divUp(bound, 128), 128, 0, stream>>>((int)bound, q[cur], n, s.children, s.nodeLo, s.nodeHi, s.size, s.parent, s.leafPos, s.firstPos,
                                                              root, s.orderedIds, outNodes, orderedIds8, q[cur ^ 1], counters, levelCount + levels, decision);
       cur ^= 1;
       bound = std::min<size_t>(bound * 8, (size_t)std::max(n / 2, 1));

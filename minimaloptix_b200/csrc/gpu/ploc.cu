@@ -23,9 +23,9 @@ constexpr int PL_TAIL = 1024;      // at most this many clusters: the single-blo
 constexpr int PL_MAX_ITERS = 250;  // state slots (a 10 M-primitive build takes ~40 iterations)
 constexpr int PL_BATCH = 8;        // iterations enqueued between two host read-backs
 
-// Loop state of the clustering, one slot per iteration, in device memory: iteration `it` reads slot it and its scan
-// kernel writes slot it+1, so the host can enqueue PL_BATCH iterations back to back — grids sized for the last
-// count it knows (counts only shrink; surplus blocks return at once) — and read one slot back per batch instead of
+// Loop state of the clustering, one slot per iteration, in device memory: iteration `it` reads slot it and its merge
+// kernel (the block of the last tile) writes slot it+1, so the host can enqueue PL_BATCH iterations back to back —
+// grids sized for the last count it knows (counts only shrink; surplus blocks return at once) — and read one slot back per batch instead of
 // one count per iteration.  An iteration whose slot says count <= PL_TAIL does nothing.
 }  // namespace
 struct PlocState { int count; uint32_t nodeBase; uint32_t iters; uint32_t pad; };
@@ -112,42 +112,12 @@ __global__ void __launch_bounds__(PL_THREADS) k_ploc_tile_sums(const PlocState* 
   if (threadIdx.x == 0) tileSums[blockIdx.x] = t;
 }
 
-// single block: exclusive scan of the tile sums in place; the totals (clusters left, nodes created) advance the
-// loop state: st[0] is this iteration's slot, st[1] the next one's
-__global__ void __launch_bounds__(1024) k_ploc_scan_tiles(PlocState* __restrict__ st, unsigned long long* __restrict__ tileSums) {
-  __shared__ unsigned long long sh[1024];
-  const int n = st->count;
-  if (n <= PL_TAIL) { if (threadIdx.x == 0) st[1] = st[0]; return; }
-  const int nTiles = (n + PL_TILE - 1) / PL_TILE;
-  unsigned long long carry = 0;
-  for (int base = 0; base < nTiles; base += 1024) {
-    int i = base + threadIdx.x;
-    unsigned long long v = i < nTiles ? tileSums[i] : 0ull;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      unsigned long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0ull;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < nTiles) tileSums[i] = carry + sh[threadIdx.x] - v;
-    carry += sh[1023];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    PlocState nx;
-    nx.count = (int)(carry & 0xffffffffull);
-    nx.nodeBase = st->nodeBase + (uint32_t)(carry >> 32);
-    nx.iters = st->iters + 1u;
-    nx.pad = 0u;
-    st[1] = nx;
-  }
-}
-
-// merge mutual pairs and compact: new cluster arrays, new inner nodes
+// merge mutual pairs and compact: new cluster arrays, new inner nodes.  Every block sums the tile totals in front of
+// it itself (at most 10 K values of 8 bytes, L2-resident) — no scan kernel between the two — and the block of the
+// last tile, which then knows the grand totals, advances the loop state: st[0] is this iteration's slot, st[1] the
+// next one's.
 __global__ void __launch_bounds__(PL_THREADS)
-k_ploc_merge(const PlocState* __restrict__ st, int nLeaves, const uint32_t* __restrict__ nn, const unsigned long long* __restrict__ tileOffsets,
+k_ploc_merge(PlocState* __restrict__ st, int nLeaves, const uint32_t* __restrict__ nn, const unsigned long long* __restrict__ tileSums,
              const uint32_t* __restrict__ cidIn, const float4* __restrict__ cLoIn, const float4* __restrict__ cHiIn,
              uint32_t* __restrict__ cidOut, float4* __restrict__ cLoOut, float4* __restrict__ cHiOut,
              float4* __restrict__ nodeLo, float4* __restrict__ nodeHi, uint2* __restrict__ children, uint32_t* __restrict__ parent,
@@ -155,8 +125,15 @@ k_ploc_merge(const PlocState* __restrict__ st, int nLeaves, const uint32_t* __re
   __shared__ unsigned long long sh[PL_THREADS / 32];
   __shared__ unsigned long long warpOff[PL_THREADS / 32];
   const int n = st->count;
-  if (n <= PL_TAIL || blockIdx.x * PL_TILE >= n) return;
+  if (n <= PL_TAIL) { if (blockIdx.x == 0 && threadIdx.x == 0) st[1] = st[0]; return; }   // nothing left to do here
+  if (blockIdx.x * PL_TILE >= n) return;
   const uint32_t nodeBase = st->nodeBase;
+  unsigned long long tileOffset;
+  {
+    unsigned long long part = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += PL_THREADS) part += tileSums[t];
+    tileOffset = blockReduce(part, sh);
+  }
   const int base = blockIdx.x * PL_TILE + threadIdx.x * PL_ITEMS;
   unsigned long long f[PL_ITEMS], v = 0;
 #pragma unroll
@@ -173,9 +150,18 @@ k_ploc_merge(const PlocState* __restrict__ st, int nLeaves, const uint32_t* __re
   if (threadIdx.x == 0) {
     unsigned long long run = 0;
     for (int w = 0; w < PL_THREADS / 32; ++w) { warpOff[w] = run; run += sh[w]; }
+    if ((int)blockIdx.x == (n + PL_TILE - 1) / PL_TILE - 1) {   // last tile: totals of the iteration
+      const unsigned long long total = tileOffset + run;
+      PlocState nx;
+      nx.count = (int)(total & 0xffffffffull);
+      nx.nodeBase = nodeBase + (uint32_t)(total >> 32);
+      nx.iters = st->iters + 1u;
+      nx.pad = 0u;
+      st[1] = nx;
+    }
   }
   __syncthreads();
-  unsigned long long off = tileOffsets[blockIdx.x] + warpOff[warp] + incl - v;
+  unsigned long long off = tileOffset + warpOff[warp] + incl - v;
 #pragma unroll
   for (int k = 0; k < PL_ITEMS; ++k) {
     int i = base + k;
@@ -292,13 +278,22 @@ __device__ __forceinline__ uint32_t leftmostPos(uint32_t node, uint32_t root, in
 
 __global__ void k_ploc_leaf_order(int nLeaves, uint32_t root, const uint32_t* __restrict__ parent, const uint2* __restrict__ children,
                                   const uint32_t* __restrict__ size, const uint32_t* __restrict__ sortedIds,
-                                  uint32_t* __restrict__ leafPos, uint32_t* __restrict__ orderedIds, uint32_t* __restrict__ maxDepth) {
+                                  uint32_t* __restrict__ leafPos, uint32_t* __restrict__ orderedIds, uint32_t* __restrict__ firstPos,
+                                  uint32_t* __restrict__ maxDepth) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t depth = 0;
   if (i < nLeaves) {
     uint32_t pos = leftmostPos((uint32_t)i, root, nLeaves, parent, children, size, &depth);
     leafPos[i] = pos;
     orderedIds[pos] = sortedIds[i];
+    // this leaf is the leftmost one of every ancestor it reaches through left links only: each inner node gets the
+    // position of its first primitive from exactly one leaf, and nobody walks to the root for it again
+    for (uint32_t node = (uint32_t)i; node != root;) {
+      const uint32_t p = parent[node];
+      if (children[p - nLeaves].x != node) break;
+      firstPos[p - nLeaves] = pos;
+      node = p;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, o));
   if ((threadIdx.x & 31) == 0 && depth) atomicMax(maxDepth, depth);
@@ -308,7 +303,7 @@ __global__ void k_ploc_leaf_order(int nLeaves, uint32_t root, const uint32_t* __
 // and the top of the tree is contiguous.  Subtrees of <= MOX_LEAF_MAX prims fold into one leaf.
 __global__ void k_ploc_emit(int nLeaves, int nInner, uint32_t root, const uint32_t* __restrict__ parent,
                             const uint2* __restrict__ children, const uint32_t* __restrict__ size,
-                            const uint32_t* __restrict__ leafPos, const float4* __restrict__ nodeLo,
+                            const uint32_t* __restrict__ leafPos, const uint32_t* __restrict__ firstPos, const float4* __restrict__ nodeLo,
                             const float4* __restrict__ nodeHi, BvhNode2* __restrict__ out) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nInner) return;
@@ -324,7 +319,7 @@ __global__ void k_ploc_emit(int nLeaves, int nInner, uint32_t root, const uint32
     } else {
       uint32_t cnt = size[c[s]];
       if (cnt <= MOX_LEAF_MAX) {
-        uint32_t first = leftmostPos(c[s], root, nLeaves, parent, children, size);
+        uint32_t first = firstPos[c[s] - nLeaves];
         ref[s] = ~((int)(first << 3) | (int)(cnt - 1));
       } else {
         ref[s] = nInner - 1 - (int)(c[s] - nLeaves);
@@ -347,9 +342,9 @@ inline int divUp(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 size_t plocScratchBytes(int n) {
   const size_t nn = (size_t)std::max(n, 2);
-  // 2 cid + nn + parent(2) + size(2) + leafPos + orderedIds = 9 words, 4 cluster boxes + 2x2 node boxes = 8 float4,
+  // 2 cid + nn + parent(2) + size(2) + leafPos + orderedIds + firstPos = 10 words, 4 cluster boxes + 2x2 node boxes = 8 float4,
   // children 8 B, tile sums; plus alignment slack for 16 slices
-  return nn * (9 * 4 + 8 * 16 + 8) + (size_t)(divUp(nn, PL_TILE) + 2) * 8 + (size_t)(PL_MAX_ITERS + 1) * sizeof(PlocState) + 17 * 256;
+  return nn * (10 * 4 + 8 * 16 + 8) + (size_t)(divUp(nn, PL_TILE) + 2) * 8 + (size_t)(PL_MAX_ITERS + 1) * sizeof(PlocState) + 17 * 256;
 }
 
 bool plocAlloc(PlocScratch& s, int n, DeviceArena& a, std::string& err) {
@@ -361,11 +356,11 @@ bool plocAlloc(PlocScratch& s, int n, DeviceArena& a, std::string& err) {
   s.nodeLo = a.take<float4>(2 * nn); s.nodeHi = a.take<float4>(2 * nn);
   s.children = a.take<uint2>(nn);
   s.parent = a.take<uint32_t>(2 * nn); s.size = a.take<uint32_t>(2 * nn);
-  s.leafPos = a.take<uint32_t>(nn); s.orderedIds = a.take<uint32_t>(nn);
+  s.leafPos = a.take<uint32_t>(nn); s.orderedIds = a.take<uint32_t>(nn); s.firstPos = a.take<uint32_t>(nn);
   s.tileSums = a.take<unsigned long long>((size_t)divUp(nn, PL_TILE) + 2);
   s.state = a.take<PlocState>(PL_MAX_ITERS + 1);
   s.hostTotal = a.pinned;
-  if (!s.tileSums || !s.state || !s.hostTotal) { err = "PLOC scratch does not fit the build arena"; return false; }
+  if (!s.tileSums || !s.state || !s.firstPos || !s.hostTotal) { err = "PLOC scratch does not fit the build arena"; return false; }
   return true;
 }
 
@@ -395,7 +390,6 @@ bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* p
       const int c = it & 1;
       k_ploc_nn<<<divUp(count, PL_THREADS), PL_THREADS, 0, stream>>>(st + it, radius, s.cLo[c], s.cHi[c], s.nn);
       k_ploc_tile_sums<<<nTiles, PL_THREADS, 0, stream>>>(st + it, s.nn, s.tileSums);
-      k_ploc_scan_tiles<<<1, 1024, 0, stream>>>(st + it, s.tileSums);
       k_ploc_merge<<<nTiles, PL_THREADS, 0, stream>>>(st + it, n, s.nn, s.tileSums, s.cid[c], s.cLo[c], s.cHi[c],
                                                        s.cid[c ^ 1], s.cLo[c ^ 1], s.cHi[c ^ 1], s.nodeLo, s.nodeHi, s.children,
                                                        s.parent, s.size);
@@ -422,8 +416,8 @@ bool plocBuild(PlocScratch& s, int n, const uint32_t* sortedIds, const float4* p
   const uint32_t root = (uint32_t)(n + nInner - 1);
   uint32_t* dDepth = (uint32_t*)(dTotal + 1);
   PCK(cudaMemsetAsync(dDepth, 0, 4, stream));
-  k_ploc_leaf_order<<<divUp(n, B), B, 0, stream>>>(n, root, s.parent, s.children, s.size, sortedIds, s.leafPos, s.orderedIds, dDepth);
-  k_ploc_emit<<<divUp(nInner, B), B, 0, stream>>>(n, nInner, root, s.parent, s.children, s.size, s.leafPos, s.nodeLo, s.nodeHi, outNodes);
+  k_ploc_leaf_order<<<divUp(n, B), B, 0, stream>>>(n, root, s.parent, s.children, s.size, sortedIds, s.leafPos, s.orderedIds, s.firstPos, dDepth);
+  k_ploc_emit<<<divUp(nInner, B), B, 0, stream>>>(n, nInner, root, s.parent, s.children, s.size, s.leafPos, s.firstPos, s.nodeLo, s.nodeHi, outNodes);
   float4 lo, hi;
   PCK(cudaMemcpyAsync(&lo, s.nodeLo + root, 16, cudaMemcpyDeviceToHost, stream));
   PCK(cudaMemcpyAsync(&hi, s.nodeHi + root, 16, cudaMemcpyDeviceToHost, stream));
