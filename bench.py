@@ -234,7 +234,8 @@ def main():
     ctx.set_partition(rank, world, TILE)
     if args.emulate_world > 1 and world == 1:
         ctx.set_partition(0, args.emulate_world, TILE)
-    build_ms = ctx.build_accel()
+    ctx.build_accel()              # warm-up build: loads the build kernels (lazy module loading), sizes the arena
+    build_ms = ctx.build_accel()   # the build that is reported (CUDA events around the build kernels)
     cam = sc.cam_params(W, H)
 
     tiles = TileGather(ctx, rank, world, dev)

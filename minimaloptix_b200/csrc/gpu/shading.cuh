@@ -43,6 +43,8 @@ MOX_D float sqr(float x) { return x * x; }
 template <bool F> MOX_D float bdiv(float a, float b) { return F ? __fdividef(a, b) : a / b; }
 template <bool F> MOX_D float bpow(float x, float y) { return F ? __powf(x, y) : powf(x, y); }   // ex2(y * lg2(x)): NaN for x < 0 like powf
 template <bool F> MOX_D float blog(float x) { return F ? __logf(x) : logf(x); }
+// normalize for vectors that only enter BRDF values (half vector of a light sample, tangent frame of the anisotropic lobe)
+template <bool F> MOX_D float3 bnormalize(const float3& v) { return F ? v * rsqrtf(dot(v, v)) : normalize(v); }
 template <bool F> MOX_D float bsqrt(float x) {
   if (!F) return sqrtf(x);
   float r;
@@ -126,8 +128,8 @@ struct DisneyHit {
     ax = r5.x; ay = r5.y; clearcoatAlpha = r5.z; specularAlpha = r5.w;
     diffuseRatio = r6.x; pdfRatio = r6.y;
     Onb3 onb(N);
-    X = normalize(onb.tangent);
-    Y = normalize(cross(N, X));
+    X = bnormalize<F>(onb.tangent);
+    Y = bnormalize<F>(cross(N, X));
   }
 
   MOX_D DisneyHit(const DisneyParams& mp, const float3& baseColor, const float3& n) {
@@ -141,8 +143,8 @@ struct DisneyHit {
     float aspect = sqrtf(1 - mp.anisotropic * 0.9f);
     ax = fmaxf(.001f, sqr(mp.roughness) / aspect);
     ay = fmaxf(.001f, sqr(mp.roughness) * aspect);
-    X = normalize(onb.tangent);
-    Y = normalize(cross(N, X));
+    X = bnormalize<F>(onb.tangent);
+    Y = bnormalize<F>(cross(N, X));
     metallic = mp.metallic; subsurface = mp.subsurface; roughness = mp.roughness; sheen = mp.sheen; clearcoat = mp.clearcoat;
     clearcoatAlpha = lerpf(0.1f, 0.001f, mp.clearcoatGloss);
     specularAlpha = fmaxf(0.001f, mp.roughness);

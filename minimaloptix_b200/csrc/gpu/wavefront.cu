@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_MINBLOCKS) k_shade_disn
       float3 contrib = mk3(0.f);
       if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
         shadowCount++;
-        H = normalize(L + V);
+        H = bnormalize<F>(L + V);
         float lightPdf = bdiv<F>(bdiv<F>(lightDst * lightDst, __ldg(&lp->area)), dot(normalOnLight, -L));
         float dr;
         float objPdf = dh.pdf(L, H, dr);
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(DISNEY_TPB, MOX_DISNEY_NEE_MINBLOCKS) k_disney
     float3 contrib = mk3(0.f);
     if (dot(L, N) > 0.f && dot(L, normalOnLight) < 0.f) {
       shadowCount++;
-      H = normalize(L + V);
+      H = bnormalize<F>(L + V);
       float lightPdf = bdiv<F>(bdiv<F>(lightDst * lightDst, __ldg(&lp->area)), dot(normalOnLight, -L));
       float dr;
       float objPdf = dh.pdf(L, H, dr);

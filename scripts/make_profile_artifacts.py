@@ -32,32 +32,37 @@ with open(out("launch_shares.csv"), "w") as f:
         f.write(f"{k},{n},{us:.1f},{us / total:.4f}\n")
 print(open(out("launch_shares.csv")).read())
 
-# ---- full capture -> summary + traffic
-rep = os.path.join(ROOT, "gpurun_out", f"prof_{src_tag}.ncu-rep")
-summary = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
-open(out("kernels_summary.txt"), "w").write(summary)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
-h, units, data = rr[0], rr[1], rr[2:]
-col = {n: h.index(n) for n in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "lts__t_bytes.sum") if n in h}
-scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+# ---- full captures (raw-page CSVs of the traversal and of the shading kernels) -> summary + traffic
+summary = ""
+scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+tscale = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}
 key_of = lambda n: ("k_traverse_closest" if "k_traverse_wide<0" in n else "k_traverse_shadow" if "k_traverse_wide<1" in n
                     else "k_shade_disney" if "k_shade_disney" in n else "k_classify" if "k_classify" in n else "k_logic" if "k_logic" in n
                     else "k_apply" if "k_apply" in n else "k_accumulate" if "k_accumulate" in n else "k_generate" if "k_generate" in n else None)
 acc = {}
-for r in data:
-    k = key_of(r[col["Kernel Name"]])
-    if not k:
+for part in ("trav", "shade"):
+    f = os.path.join(ROOT, "gpurun_out", f"prof_{src_tag}_{part}_raw.csv")
+    if not os.path.exists(f):
         continue
-    b = sum(float(r[col[c]]) * scale[units[col[c]]] for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    a = acc.setdefault(k, {"kernel": r[col["Kernel Name"]][:64], "launches_profiled": 0, "dram_bytes_per_launch": 0.0,
-                           "lts_bytes_per_launch": 0.0, "ms_per_launch_under_ncu": 0.0})
-    a["launches_profiled"] += 1
-    a["dram_bytes_per_launch"] += b
-    if "lts__t_bytes.sum" in col:
-        a["lts_bytes_per_launch"] += float(r[col["lts__t_bytes.sum"]]) * scale[units[col["lts__t_bytes.sum"]]]
-    tu = units[col["gpu__time_duration.sum"]]
-    a["ms_per_launch_under_ncu"] += float(r[col["gpu__time_duration.sum"]]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(tu, 1.0)
+    summary += f"== {part}: ncu --set full --metrics lts__t_bytes.sum --clock-control none, launches of one step, {spp} spp per wavefront ==\n"
+    summary += subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), f], capture_output=True, text=True).stdout
+    rows_ = [r for r in csv.reader(open(f)) if r]
+    st = [i for i, r in enumerate(rows_) if r[0] == "ID"][0]
+    h, units, data = rows_[st], rows_[st + 1], rows_[st + 2:]   # units are per column AND per file
+    col = {n: h.index(n) for n in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "lts__t_bytes.sum") if n in h}
+    val = lambda r, c: float(r[col[c]]) * scale[units[col[c]]]
+    for r in data:
+        k = key_of(r[col["Kernel Name"]])
+        if not k:
+            continue
+        a = acc.setdefault(k, {"kernel": r[col["Kernel Name"]][:64], "launches_profiled": 0, "dram_bytes_per_launch": 0.0,
+                               "lts_bytes_per_launch": 0.0, "ms_per_launch_under_ncu": 0.0})
+        a["launches_profiled"] += 1
+        a["dram_bytes_per_launch"] += val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+        if "lts__t_bytes.sum" in col:
+            a["lts_bytes_per_launch"] += val(r, "lts__t_bytes.sum")
+        a["ms_per_launch_under_ncu"] += float(r[col["gpu__time_duration.sum"]]) * tscale.get(units[col["gpu__time_duration.sum"]], 1.0)
+open(out("kernels_summary.txt"), "w").write(summary)
 for a in acc.values():
     for k in ("dram_bytes_per_launch", "lts_bytes_per_launch", "ms_per_launch_under_ncu"):
         a[k] /= a["launches_profiled"]
