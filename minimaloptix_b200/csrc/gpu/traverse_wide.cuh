@@ -122,13 +122,23 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
     while (true) {
       const bool isTri = active && tBits != 0u;
       const bool isNode = active && !isTri && (gBits & 0xff000000u) != 0u;
-      const unsigned nm = __ballot_sync(FULL, isNode), tm = __ballot_sync(FULL, isTri);
-      const int nNode = __popc(nm), nTri = __popc(tm);  // disjoint masks: busy lanes = nNode + nTri (POPC shares the slow conversion pipe)
-      if ((nm | tm) == 0u || (!exhausted && nNode + nTri < job.fetchThreshold)) break;
 #ifndef MOX_VOTE_TRI_WEIGHT
 #define MOX_VOTE_TRI_WEIGHT 4  // a primitive step costs less than half a node step: vote by cost, not by head count (measured 1: 1115, 2: 1191, 3: 1206, 4: 1214, 6: 1207, 32: 1069 Mrays/s)
 #endif
+#ifndef MOX_VOTE_POPC
+      // one ballot + one warp reduction (REDUX) of the weighted vote instead of two ballots + two POPCs — POPC shares the
+      // slow conversion pipe with the 48 I2F of a node step (ncu: 15-19 % of the stall samples are mio_throttle):
+      // extend 71.6 -> 71.0 ms, shadow 92.2 -> 91.7 ms per step (MOX_VOTE_POPC restores the counted form)
+      const unsigned bm = __ballot_sync(FULL, isNode | isTri);
+      const int score = __reduce_add_sync(FULL, isNode ? 1 : (isTri ? -MOX_VOTE_TRI_WEIGHT : 0));
+      if (bm == 0u || (!exhausted && __popc(bm) < job.fetchThreshold)) break;
+      if (score >= 0) {
+#else
+      const unsigned nm = __ballot_sync(FULL, isNode), tm = __ballot_sync(FULL, isTri);
+      const int nNode = __popc(nm), nTri = __popc(tm);  // disjoint masks: busy lanes = nNode + nTri (POPC shares the slow conversion pipe)
+      if ((nm | tm) == 0u || (!exhausted && nNode + nTri < job.fetchThreshold)) break;
       if (nNode >= MOX_VOTE_TRI_WEIGHT * nTri) {
+#endif
         if (isNode) {
           // ---- pop the front-most pending child of G
           const uint32_t bit = 31u - (uint32_t)__clz(gBits & 0xff000000u);
