@@ -411,7 +411,8 @@ int sliceEnqueueExtend(mox_ctx* c, mox_ctx::Slice& sl) {
   // bounce's counter block, `bound` (what was shaded) only sizes the grids
   const uint32_t* countPtr = depth == 1 ? nullptr : bounceBlock(sl.pb, depth - 1) + C_NEXT;
   tm.begin(ST_EXTEND, sl.stream, depth);
-  launchExtend(lc, lc.pb.qCur, sl.bound, countPtr, depth);
+  // camera rays are queued in path order (k_generate: qCur[p] = p): the traversal kernel skips the indirection
+  launchExtend(lc, depth == 1 ? nullptr : lc.pb.qCur, sl.bound, countPtr, depth);
   tm.end(sl.stream);
   tm.begin(ST_SHADE, sl.stream);
   launchClassify(lc, lc.pb.qCur, sl.bound, countPtr, depth);
