@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define MOX_TRAV_TPB 128   // threads per CTA of the persistent traversal kernels
+
 // One batch of rays for the persistent traversal kernel.
 //   rayO[id] = (origin, tmin)   rayD[id] = (direction, tmax); tmax < 0 marks an unused slot
 //   queue    : optional indirection, ray id = queue[i] for i < count

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(TPB) k_generate(LaunchCtx c, uint32_t nPaths) 
 }
 
 // ------------------------------------------------------------------ traversal + classify
-constexpr int TRAV_TPB = 128;
+constexpr int TRAV_TPB = MOX_TRAV_TPB;
 #ifndef MOX_TRAV_MINBLOCKS
 #define MOX_TRAV_MINBLOCKS 10  // caps the kernel at 48 registers: measured 983 (55 regs) -> 1022 Mrays/s; 12 blocks (40 regs): 1005
 #endif
