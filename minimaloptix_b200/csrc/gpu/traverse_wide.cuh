@@ -68,7 +68,9 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   // Per-lane state.  A lane is busy exactly while it has a primitive group or a node group pending (a ray with
   // neither pops its stack or finishes in the same iteration), so there is no separate "active" flag.  CLASSIFY keeps
   // the winner's shade class in bits 28..30 of bPrim (the form the hit record has anyway).  A shadow ray's
-  // transmittance lives in shared memory: it is touched only when a ray meets tinting glass.
+  // transmittance lives in the last two entries of the lane's stack array (local memory, no L1 footprint until
+  // touched): it is needed only when a ray meets tinting glass.  (Shared memory for it cost L1: the carve-out is
+  // permanent; 2.5 KB per CTA lowered the shadow kernel's L1 hit rate by a point.)
   uint2 stack[MOX_WIDE_STACK];
   int sp = 0;
   uint32_t gBase = 0, gBits = 0;  // node group
@@ -78,9 +80,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   float3 o = mk3(0.f), d = mk3(0.f), idir = mk3(0.f);
   float tmin = 0.f, tBest = 0.f, bBeta = 0.f, bGamma = 0.f;
   int bPrim = -1;
-  bool tinted = false;               // ANYHIT: sAtten holds a product of glass colours for this ray
+  bool tinted = false;               // ANYHIT: the top of the stack array holds a product of glass colours for this ray
   uint32_t shadowEnd = 0;            // ANYHIT && COUNT: 1 blocked, 2 tinted
-  __shared__ float sAtten[ANYHIT ? 3 : 1][ANYHIT ? MOX_TRAV_TPB : 1];
   uint32_t nv = 0, np = 0;
 #define MOX_LANE_BUSY() (tBits != 0u || (gBits & 0xff000000u) != 0u)
   WtRay wr;
@@ -311,9 +312,14 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
               } else if (cls == MOX_SHADOW_TINTS) {
                 const GpuMaterial* m = s.mats + (__ldg(&s.prims[id].typeMat) >> 2);
                 const float3 col = mk3(__ldg(&m->dis.color.x), __ldg(&m->dis.color.y), __ldg(&m->dis.color.z));
-                const int tl = threadIdx.x;
-                if (!tinted) { sAtten[0][tl] = 1.f * col.x; sAtten[1][tl] = 1.f * col.y; sAtten[2][tl] = 1.f * col.z; tinted = true; }
-                else { sAtten[0][tl] *= col.x; sAtten[1][tl] *= col.y; sAtten[2][tl] *= col.z; }
+                float3 a = col;   // = (1, 1, 1) * col
+                if (tinted) {
+                  const uint2 p0 = stack[MOX_WIDE_STACK - 2], p1 = stack[MOX_WIDE_STACK - 1];
+                  a = mk3(__uint_as_float(p0.x) * col.x, __uint_as_float(p0.y) * col.y, __uint_as_float(p1.x) * col.z);
+                }
+                stack[MOX_WIDE_STACK - 2] = make_uint2(__float_as_uint(a.x), __float_as_uint(a.y));
+                stack[MOX_WIDE_STACK - 1] = make_uint2(__float_as_uint(a.z), 0u);
+                tinted = true;
               }
             } else {
               tBest = t;
@@ -334,8 +340,9 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
             // unoccluded: the contribution stays as the shade kernel wrote it; blocked: already zeroed at the hit;
             // only a ray tinted by glass needs the read-modify-write (the load stalls the whole warp)
             if (tinted) {
+              const uint2 p0 = stack[MOX_WIDE_STACK - 2], p1 = stack[MOX_WIDE_STACK - 1];
               float4 c = MOX_LD_STREAM(job.shC + rayId);
-              MOX_ST_STREAM(job.shC + rayId, make_float4(c.x * sAtten[0][threadIdx.x], c.y * sAtten[1][threadIdx.x], c.z * sAtten[2][threadIdx.x], c.w));
+              MOX_ST_STREAM(job.shC + rayId, make_float4(c.x * __uint_as_float(p0.x), c.y * __uint_as_float(p0.y), c.z * __uint_as_float(p1.x), c.w));
               tinted = false;
               if (COUNT) shadowEnd = 2u;
             }
