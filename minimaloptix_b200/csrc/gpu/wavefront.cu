@@ -740,22 +740,29 @@ static unsigned persistentGridFor(K kernel, uint32_t count, std::atomic<int>& bl
   return need < full ? need : full;
 }
 
-// closest-hit rays refill earlier than shadow rays (measured on the bench scene: closest 20 -> 24: 235 -> 231 ms,
-// shadow 20 -> 24: 313 -> 315 ms per step)
+// Busy lanes below which a warp refills.  Closest hit: 24 (20: 70.2, 24: 69.1, 28: 71.0 ms of extend per step).
+// Shadow rays on the wide BVH claim their ray ids in chunks, which makes a refill cheap (one memory level): 24 there
+// too (16: 93.9, 20: 89.8, 24: 86.7, 26: 86.9, 28: 88.2, 32: 100.6 ms of shadow per step); the binary kernel, which
+// pays an atomic and a queue load per refill, stays at 20.
 #ifndef MOX_FETCH_THRESHOLD_CLOSEST
 #define MOX_FETCH_THRESHOLD_CLOSEST 24
 #endif
-static int fetchThreshold(bool anyHit) {
-  struct T { int t[2]; };
+#ifndef MOX_FETCH_THRESHOLD_SHADOW_WIDE
+#define MOX_FETCH_THRESHOLD_SHADOW_WIDE 24
+#endif
+static int fetchThreshold(bool anyHit, bool wide) {
+  struct T { int t[3]; };
   static const T v = [] {   // thread-safe one-time initialisation
     T r;
     const char* e = getenv("MOX_FETCH_THRESHOLD");
+    const char* es = getenv("MOX_FETCH_THRESHOLD_SHADOW");   // shadow rays only (A/B runs)
     r.t[0] = e ? atoi(e) : MOX_FETCH_THRESHOLD_CLOSEST;
-    r.t[1] = e ? atoi(e) : MOX_FETCH_THRESHOLD;
-    for (int k = 0; k < 2; ++k) r.t[k] = r.t[k] < 1 ? 1 : r.t[k] > 32 ? 32 : r.t[k];
+    r.t[1] = es ? atoi(es) : e ? atoi(e) : MOX_FETCH_THRESHOLD;
+    r.t[2] = es ? atoi(es) : e ? atoi(e) : MOX_FETCH_THRESHOLD_SHADOW_WIDE;
+    for (int k = 0; k < 3; ++k) r.t[k] = r.t[k] < 1 ? 1 : r.t[k] > 32 ? 32 : r.t[k];
     return r;
   }();
-  return v.t[anyHit ? 1 : 0];
+  return v.t[anyHit ? (wide ? 2 : 1) : 0];
 }
 
 template <bool ANYHIT, bool COUNT, bool CLASSIFY>
@@ -771,7 +778,7 @@ static void launchTraverseT(const SceneView& s, const TraceJob& job, cudaStream_
 void launchTraverse(const SceneView& s, const TraceJob& jobIn, bool anyHit, bool count, cudaStream_t stream, bool classify) {
   if (!jobIn.count) return;
   TraceJob job = jobIn;
-  job.fetchThreshold = fetchThreshold(anyHit);
+  job.fetchThreshold = fetchThreshold(anyHit, s.nodes8 != nullptr);
   job.originMagic = job.originMod ? (uint32_t)(0x100000000ull / job.originMod) + 1u : 0u;
   cudaMemsetAsync(job.cursor, 0, 4, stream);
   if (anyHit && count) launchTraverseT<true, true, false>(s, job, stream);
