@@ -95,6 +95,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   // per refill.
 #ifdef MOX_REFILL_PER_EVENT
   constexpr bool CHUNKED = false;
+#elif defined(MOX_REFILL_CHUNK_ALL)
+  constexpr bool CHUNKED = true;
 #else
   constexpr bool CHUNKED = ANYHIT;
 #endif
