@@ -216,6 +216,7 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
   // ---- emit
   uint32_t meta[8], qlx[8], qly[8], qlz[8], qhx[8], qhy[8], qhz[8];
   uint32_t innerRank = 0, primOff = 0;
+  uint32_t validPrims = 0;   // fixed-slot layout: bits 2s, 2s + 1 = the primitives of the leaf child in slot s
   for (int s = 0; s < 8; ++s) {
     int i = childAt[s];
     if (i < 0) {  // empty slot: inverted box, never hit
@@ -247,13 +248,19 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
       else first = firstPos[c - nLeaves];   // leaf-order position of the subtree's first primitive (k_ploc_leaf_order)
       for (uint32_t k = 0; k < cnt; ++k) orderedIds8[primBase + primOff + k] = orderedIds[first + k];
       meta[s] = (((1u << cnt) - 1u) << 5) | primOff;
+      validPrims |= ((1u << cnt) - 1u) << (2 * s);
       primOff += cnt;
     }
   }
   auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
   BvhNode8 nd;
   nd.n0 = make_float4(blo.x, blo.y, blo.z, __uint_as_float(ex | (ey << 8) | (ez << 16) | (imask << 24)));
+#ifdef MOX_NODE_META
   nd.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
+#else
+  nd.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float((imask << 24) | validPrims),
+                      __uint_as_float((validPrims << 8) | imask));
+#endif
   nd.n2 = make_float4(__uint_as_float(pack4(qlx)), __uint_as_float(pack4(qlx + 4)), __uint_as_float(pack4(qly)), __uint_as_float(pack4(qly + 4)));
   nd.n3 = make_float4(__uint_as_float(pack4(qlz)), __uint_as_float(pack4(qlz + 4)), __uint_as_float(pack4(qhx)), __uint_as_float(pack4(qhx + 4)));
   nd.n4 = make_float4(__uint_as_float(pack4(qhy)), __uint_as_float(pack4(qhy + 4)), __uint_as_float(pack4(qhz)), __uint_as_float(pack4(qhz + 4)));

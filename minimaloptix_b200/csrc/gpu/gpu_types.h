@@ -52,10 +52,16 @@ static_assert(sizeof(BvhNode2) == 64, "BvhNode2");
 // Compressed 8-wide node (after Ylitie, Karras, Laine 2017), 80 bytes = 5 x float4, 16-byte aligned:
 //   n0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16 | imask << 24)   p: box minimum; e*: biased exponents of the
 //        per-axis grid scale 2^(e-127); imask bit s: the child in slot s is an inner node
-//   n1 = (childBase, primBase, meta[0..3], meta[4..7])
+//   n1 = (childBase, primBase, valid, group)
 //        inner children are stored contiguously from childBase in slot order; the primitives of all leaf
-//        children are contiguous from primBase in the wide-leaf-ordered packed array
-//        meta: 0 = empty; inner: 0b001 << 5 | (24 + slot); leaf: unary count (1..3) << 5 | offset from primBase
+//        children are contiguous from primBase in the wide-leaf-ordered packed array, in slot order.
+//        Hit bits have FIXED positions per slot s: bit 24 + s = "the inner child in slot s is hit", bits 2s and
+//        2s + 1 = "primitive 0 / 1 of the leaf child in slot s is hit" (a leaf child holds <= 2 primitives), so the
+//        traversal ORs one compile-time constant per hit child and masks the result once:
+//        valid = imask << 24 | V,  V = the primitive bits that exist (16 bits);  group = V << 8 | imask (the low
+//        24 bits of the lane's node-group word).  The rank of primitive bit k among V's set bits is its offset
+//        from primBase.  (Round 1 and most of round 2 kept a position + count byte per child instead:
+//        MOX_NODE_META restores that layout, five more instructions per child in the node test.)
 //   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])      child boxes, 8 bit per plane:
 //   n3 = (qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7])      lo = p + qlo * scale (rounded down),
 //   n4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])      hi = p + qhi * scale (rounded up)
@@ -65,6 +71,9 @@ struct __align__(16) BvhNode8 { float4 n0, n1, n2, n3, n4; };
 static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
 #ifndef MOX_WIDE_LEAF_MAX
 #define MOX_WIDE_LEAF_MAX 2  // measured: 2 -> 1037, 1 -> 1036, 3 -> 1013 Mrays/s (binary BVH: 1029)
+#endif
+#if !defined(MOX_NODE_META) && MOX_WIDE_LEAF_MAX > 2
+#error "the fixed-slot node layout has two primitive bits per slot: MOX_WIDE_LEAF_MAX > 2 needs MOX_NODE_META"
 #endif
 
 // Leaf-ordered packed primitive, 3 x float4 = 48 bytes per slot.

@@ -23,10 +23,11 @@
 //   b * ia + on  ==  m * (2^15 ia) + (on - 2^15 ia)
 // The addend's rounding error (<= 2^-24 of 2^15 |ia|, i.e. 2^-9 of one quantisation step) is added to the
 // conservative margin, so boxes only ever grow.
-#ifdef MOX_BYTE_PRMT
+// MOX_BYTE_HYBRID converts the near planes with I2F and the far planes with PRMT: half the load on either pipe.
+#if defined(MOX_BYTE_PRMT) || defined(MOX_BYTE_HYBRID)
 // `one` is 1.0f's bit pattern held in a register (see traverseWidePersistent): with the constant as an immediate
 // ptxas needs the byte selector in a register and re-materialises four selectors per node.
-MOX_D float byteToFloat(uint32_t w, int i, uint32_t one) {
+MOX_D float byteToFloatPrmt(uint32_t w, int i, uint32_t one) {
   uint32_t r;
   if (i == 0) asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(one));
   else if (i == 1) asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(one));
@@ -34,11 +35,25 @@ MOX_D float byteToFloat(uint32_t w, int i, uint32_t one) {
   else asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(one));
   return __uint_as_float(r);
 }
-#define MOX_B2F(w, i) byteToFloat(w, i, one)
-#else
-MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
-#define MOX_B2F(w, i) byteToFloat(w, i)
 #endif
+MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+#if defined(MOX_BYTE_PRMT)
+#define MOX_B2F_NEAR(w, i) byteToFloatPrmt(w, i, one)
+#define MOX_B2F_FAR(w, i) byteToFloatPrmt(w, i, one)
+#elif defined(MOX_BYTE_HYBRID)
+#define MOX_B2F_NEAR(w, i) byteToFloat(w, i)
+#define MOX_B2F_FAR(w, i) byteToFloatPrmt(w, i, one)
+#else
+#define MOX_B2F_NEAR(w, i) byteToFloat(w, i)
+#define MOX_B2F_FAR(w, i) byteToFloat(w, i)
+#endif
+
+// (a & m) | (b & ~m) as one LOP3 (written as two ANDs and an OR, ptxas spends two)
+MOX_D uint32_t bitSelect(uint32_t a, uint32_t b, uint32_t m) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(a), "r"(b), "r"(m));
+  return r;
+}
 
 // CLASSIFY (closest hit of the render path): the hit record is (t, primitive id | shade class << 28) — the class
 // comes from the winning primitive's packed record — and beta / gamma are not carried (two registers less per
@@ -61,7 +76,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
     __syncthreads();
   }
 #endif
-#ifdef MOX_BYTE_PRMT
+#if defined(MOX_BYTE_PRMT) || defined(MOX_BYTE_HYBRID)
   // 0x3f800000 that ptxas cannot fold into an immediate (a launch never has 2^31 rays)
   const uint32_t one = 0x3f800000u | (job.count >> 31);
 #endif
@@ -222,32 +237,50 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           // conservative: every axis gets its own rounding bound (2^-21 of the local origin term), folded
           // into separate near / far addends so the per-child cost stays one FMA per plane; the far side
           // is additionally widened by 1e-5 relative
-#ifdef MOX_BYTE_PRMT
+#if defined(MOX_BYTE_PRMT) || defined(MOX_BYTE_HYBRID)
           const float kx = iax * 32768.f, ky = iay * 32768.f, kz = iaz * 32768.f;
           const float ex_ = fmaf(2.384185791015625e-07f, fabsf(kx), 4.76837158203125e-07f * fabsf(oax));
           const float ey_ = fmaf(2.384185791015625e-07f, fabsf(ky), 4.76837158203125e-07f * fabsf(oay));
           const float ez_ = fmaf(2.384185791015625e-07f, fabsf(kz), 4.76837158203125e-07f * fabsf(oaz));
-          const float onx = (oax - ex_) - kx, ofx = (oax + ex_) - kx, ony = (oay - ey_) - ky, ofy = (oay + ey_) - ky;
-          const float onz = (oaz - ez_) - kz, ofz = (oaz + ez_) - kz;
-#define MOX_PLANE_SCALE_X kx
-#define MOX_PLANE_SCALE_Y ky
-#define MOX_PLANE_SCALE_Z kz
+          const float ofx = (oax + ex_) - kx, ofy = (oay + ey_) - ky, ofz = (oaz + ez_) - kz;
+#define MOX_FAR_SCALE_X kx
+#define MOX_FAR_SCALE_Y ky
+#define MOX_FAR_SCALE_Z kz
+#ifdef MOX_BYTE_PRMT
+          const float onx = (oax - ex_) - kx, ony = (oay - ey_) - ky, onz = (oaz - ez_) - kz;
+#define MOX_NEAR_SCALE_X kx
+#define MOX_NEAR_SCALE_Y ky
+#define MOX_NEAR_SCALE_Z kz
 #else
-          const float ex_ = 4.76837158203125e-07f * fabsf(oax), ey_ = 4.76837158203125e-07f * fabsf(oay), ez_ = 4.76837158203125e-07f * fabsf(oaz);
-          const float onx = oax - ex_, ofx = oax + ex_, ony = oay - ey_, ofy = oay + ey_, onz = oaz - ez_, ofz = oaz + ez_;
-#define MOX_PLANE_SCALE_X iax
-#define MOX_PLANE_SCALE_Y iay
-#define MOX_PLANE_SCALE_Z iaz
+          const float onx = fmaf(-4.76837158203125e-07f, fabsf(oax), oax), ony = fmaf(-4.76837158203125e-07f, fabsf(oay), oay);
+          const float onz = fmaf(-4.76837158203125e-07f, fabsf(oaz), oaz);
+#define MOX_NEAR_SCALE_X iax
+#define MOX_NEAR_SCALE_Y iay
+#define MOX_NEAR_SCALE_Z iaz
+#endif
+#else
+          // (one FMA per addend: |oa| * 2^-21 is exact, so the sum is rounded once either way)
+          const float onx = fmaf(-4.76837158203125e-07f, fabsf(oax), oax), ofx = fmaf(4.76837158203125e-07f, fabsf(oax), oax);
+          const float ony = fmaf(-4.76837158203125e-07f, fabsf(oay), oay), ofy = fmaf(4.76837158203125e-07f, fabsf(oay), oay);
+          const float onz = fmaf(-4.76837158203125e-07f, fabsf(oaz), oaz), ofz = fmaf(4.76837158203125e-07f, fabsf(oaz), oaz);
+#define MOX_NEAR_SCALE_X iax
+#define MOX_NEAR_SCALE_Y iay
+#define MOX_NEAR_SCALE_Z iaz
+#define MOX_FAR_SCALE_X iax
+#define MOX_FAR_SCALE_Y iay
+#define MOX_FAR_SCALE_Z iaz
 #endif
           uint32_t hitmask = 0;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+#ifdef MOX_NODE_META
             const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
             // four children at once: inner children (position field 24..31 = 0b11xxx) get their slot
             // XOR-ed with the ray's octant mask, which orders them front to back
             const uint32_t inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
             const uint32_t pos4 = (meta4 ^ ((inner4 >> 4) * octinv)) & 0x1f1f1f1fu;
             const uint32_t cnt4 = (meta4 >> 5) & 0x07070707u;
+#endif
             const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
             const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
             const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
@@ -256,27 +289,54 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
             const uint32_t nz = idir.z < 0.f ? qhz : qlz, fz = idir.z < 0.f ? qlz : qhz;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float tnx = fmaf(MOX_B2F(nx, i), MOX_PLANE_SCALE_X, onx), tfx = fmaf(MOX_B2F(fx, i), MOX_PLANE_SCALE_X, ofx);
-              const float tny = fmaf(MOX_B2F(ny, i), MOX_PLANE_SCALE_Y, ony), tfy = fmaf(MOX_B2F(fy, i), MOX_PLANE_SCALE_Y, ofy);
-              const float tnz = fmaf(MOX_B2F(nz, i), MOX_PLANE_SCALE_Z, onz), tfz = fmaf(MOX_B2F(fz, i), MOX_PLANE_SCALE_Z, ofz);
+              const float tnx = fmaf(MOX_B2F_NEAR(nx, i), MOX_NEAR_SCALE_X, onx), tfx = fmaf(MOX_B2F_FAR(fx, i), MOX_FAR_SCALE_X, ofx);
+              const float tny = fmaf(MOX_B2F_NEAR(ny, i), MOX_NEAR_SCALE_Y, ony), tfy = fmaf(MOX_B2F_FAR(fy, i), MOX_FAR_SCALE_Y, ofy);
+              const float tnz = fmaf(MOX_B2F_NEAR(nz, i), MOX_NEAR_SCALE_Z, onz), tfz = fmaf(MOX_B2F_FAR(fz, i), MOX_FAR_SCALE_Z, ofz);
               const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
               const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tBest)) * 1.00001f;
+#ifdef MOX_NODE_META
               // branch-free: an empty slot has count bits 0 (and an inverted box)
               const uint32_t bitsI = tn <= tf ? ((cnt4 >> (8 * i)) & 0xffu) : 0u;
               hitmask |= bitsI << ((pos4 >> (8 * i)) & 0xffu);
+#else
+              // fixed positions per slot: one select of a compile-time constant per child (gpu_types.h)
+              hitmask |= tn <= tf ? ((1u << (24 + 4 * half + i)) | (3u << (2 * (4 * half + i)))) : 0u;
+#endif
             }
           }
           gBase = __float_as_uint(n1.x);
-          gBits = (hitmask & 0xff000000u) | (ew >> 24);
           tBase = __float_as_uint(n1.y);
+#ifdef MOX_NODE_META
+          gBits = (hitmask & 0xff000000u) | (ew >> 24);
           tBits = hitmask & 0x00ffffffu;
+#else
+          // keep what exists (inner children: imask, primitives: V), then bring the inner byte into front-to-back
+          // order: bit 24 + s moves to 24 + (s ^ octinv) — three conditional swaps (nibbles, pairs, neighbours) written
+          // as shifts by 0 or 4 / 2 / 1, so there is no branch and no select: (x << 0 & m) | (x >> 0 & ~m) = x
+          hitmask &= __float_as_uint(n1.z);
+          tBits = hitmask & 0x0000ffffu;
+          {
+            const uint32_t s4 = octinv & 4u, s2 = octinv & 2u, s1 = octinv & 1u;
+            uint32_t x = hitmask;
+            x = bitSelect(x << s4, x >> s4, 0xf0000000u);
+            x = bitSelect(x << s2, x >> s2, 0xcc000000u);
+            x = bitSelect(x << s1, x >> s1, 0xaa000000u);
+            gBits = (x & 0xff000000u) | __float_as_uint(n1.w);   // n1.w = V << 8 | imask
+          }
+#endif
         }
       } else {
         if (isTri) {
           // ---- one primitive of the current group
           const uint32_t k = 31u - (uint32_t)__clz(tBits);
           tBits &= ~(1u << k);
+#ifdef MOX_NODE_META
           const float4* rec = s.packed8 + (size_t)(tBase + k) * MOX_PACKED_F4;
+#else
+          // offset from the node's first primitive = rank of bit k among the primitive bits that exist (V sits in
+          // bits 8..23 of the node-group word for as long as primitives of that node are pending)
+          const float4* rec = s.packed8 + (size_t)(tBase + __popc((gBits >> 8) & ~(0xffffffffu << k))) * MOX_PACKED_F4;
+#endif
           // All three words are fetched before the type is known: the tag is folded from words 0 and 2 and the
           // (zero) high bits of word 1, so the loads stay together ahead of the branch — waiting for word 0
           // first would put a second memory latency into every triangle test.
