@@ -15,19 +15,38 @@
 
 #define MOX_WIDE_STACK MOX_TRAVERSAL_STACK
 
-// Quantised plane byte -> float.  I2F.U8 runs on the conversion pipe (15.4 results/clk/SM measured,
-// scripts/microbench/pipe_rates.cu, against 124 FFMA): 48 conversions per node step keep that pipe ~70 % busy
-// at today's node-step rate (both traversal kernels sit at the same 42.5 G node steps/s whatever their primitive
-// load).  MOX_BYTE_PRMT instead builds m = 1 + b * 2^-15 with one PRMT on the ALU pipe — byte b dropped into
-// mantissa bits 8..15 of 1.0f — and folds the affine map back into the plane FMA:
-//   b * ia + on  ==  m * (2^15 ia) + (on - 2^15 ia)
-// The addend's rounding error (<= 2^-24 of 2^15 |ia|, i.e. 2^-9 of one quantisation step) is added to the
-// conservative margin, so boxes only ever grow.
-// MOX_BYTE_HYBRID converts the near planes with I2F and the far planes with PRMT: half the load on either pipe.
-#if defined(MOX_BYTE_PRMT) || defined(MOX_BYTE_HYBRID)
+// Quantised plane byte -> float, two ways, mixed per plane so that neither pipe is the bottleneck:
+//  * I2F.U8 on the conversion pipe (15.4 results/clk/SM measured, scripts/microbench/pipe_rates.cu, against 124
+//    FFMA): with all 48 conversions of a node step on it that pipe was ~70 % busy and 15-19 % of the stall samples
+//    were mio_throttle;
+//  * one PRMT on the ALU pipe: m = 1 + b * 2^-15 — byte b dropped into mantissa bits 8..15 of 1.0f — with the
+//    affine map folded back into the plane FMA:   b * ia + on  ==  m * (2^15 ia) + (on - 2^15 ia).
+//    The addend's rounding error (<= 2^-24 of 2^15 |ia|, i.e. 2^-9 of one quantisation step) is added to the
+//    conservative margin, so boxes only ever grow.
+// MOX_BYTE_MIX: bit 0..2 = near plane x, y, z, bit 3..5 = far plane x, y, z; a set bit converts that plane's eight
+// bytes with PRMT.  Measured (1 M-triangle bench, Mrays/s, with the select form of the hit mask): 0 (all I2F) 1 582,
+// 0x3f (all PRMT) 1 599, 0x3b 1 591, 0x38 (far planes) 1 617, 0x39 1 625, 0x30 1 633, 0x18 1 632, 0x10 1 616;
+// with MOX_HIT_SIGN=1: 0x3f 1 612, 0x10 1 627, 0x39 1 632, 0x30 1 645, 0x28 1 647, 0x33 1 648 (0x38 and 0x31 spill).
+// MOX_HIT_SIGN: how a child's box test becomes its hit bits.  0: FSETP + SEL of the child's constant, OR-ed three at
+// a time (all on the ALU pipe, which also runs the 32 FMNMX, the PRMTs and the near/far selects of a node step).
+// 1 (default): the far-side widening and the comparison are one FMA, tf * 1.00001 - tn, whose sign bit times the
+// child's constant is subtracted from an all-hit mask by one IMAD — FFMA + SHF + IMAD instead of FMUL + FSETP + SEL +
+// half an IADD3, and only the shift is on the ALU pipe.  2: the same with an arithmetic shift and one LOP3 (1 588).
+#ifndef MOX_HIT_SIGN
+#define MOX_HIT_SIGN 1
+#endif
+#ifndef MOX_BYTE_MIX
+#ifdef MOX_BYTE_PRMT
+#define MOX_BYTE_MIX 0x3f
+#else
+#define MOX_BYTE_MIX 0x33
+#endif
+#endif
 // `one` is 1.0f's bit pattern held in a register (see traverseWidePersistent): with the constant as an immediate
 // ptxas needs the byte selector in a register and re-materialises four selectors per node.
-MOX_D float byteToFloatPrmt(uint32_t w, int i, uint32_t one) {
+template <bool PRMT>
+MOX_D float byteToFloat(uint32_t w, int i, uint32_t one) {
+  if (!PRMT) return (float)((w >> (8 * i)) & 0xffu);
   uint32_t r;
   if (i == 0) asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(w), "r"(one));
   else if (i == 1) asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(w), "r"(one));
@@ -35,18 +54,17 @@ MOX_D float byteToFloatPrmt(uint32_t w, int i, uint32_t one) {
   else asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(w), "r"(one));
   return __uint_as_float(r);
 }
-#endif
-MOX_D float byteToFloat(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
-#if defined(MOX_BYTE_PRMT)
-#define MOX_B2F_NEAR(w, i) byteToFloatPrmt(w, i, one)
-#define MOX_B2F_FAR(w, i) byteToFloatPrmt(w, i, one)
-#elif defined(MOX_BYTE_HYBRID)
-#define MOX_B2F_NEAR(w, i) byteToFloat(w, i)
-#define MOX_B2F_FAR(w, i) byteToFloatPrmt(w, i, one)
-#else
-#define MOX_B2F_NEAR(w, i) byteToFloat(w, i)
-#define MOX_B2F_FAR(w, i) byteToFloat(w, i)
-#endif
+// Scale and addends of one axis for the plane FMAs  t = float(byte) * scale + addend  (near: rounded down, far:
+// rounded up): every axis gets its own rounding bound, 2^-21 of the local origin term (+ 2^-22 of the PRMT
+// form's 2^15 ia), folded into the addends so a plane costs one conversion and one FMA.
+template <bool NEAR_PRMT, bool FAR_PRMT>
+MOX_D void planeTerms(float ia, float oa, float& sn, float& an, float& sf, float& af) {
+  const float k = ia * 32768.f;
+  const float e = fmaf(2.384185791015625e-07f, fabsf(k), 4.76837158203125e-07f * fabsf(oa));
+  // (I2F form: |oa| * 2^-21 is exact, so one FMA rounds the same sum once)
+  if (NEAR_PRMT) { sn = k; an = (oa - e) - k; } else { sn = ia; an = fmaf(-4.76837158203125e-07f, fabsf(oa), oa); }
+  if (FAR_PRMT) { sf = k; af = (oa + e) - k; } else { sf = ia; af = fmaf(4.76837158203125e-07f, fabsf(oa), oa); }
+}
 
 // (a & m) | (b & ~m) as one LOP3 (written as two ANDs and an OR, ptxas spends two)
 MOX_D uint32_t bitSelect(uint32_t a, uint32_t b, uint32_t m) {
@@ -76,10 +94,8 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
     __syncthreads();
   }
 #endif
-#if defined(MOX_BYTE_PRMT) || defined(MOX_BYTE_HYBRID)
   // 0x3f800000 that ptxas cannot fold into an immediate (a launch never has 2^31 rays)
   const uint32_t one = 0x3f800000u | (job.count >> 31);
-#endif
   // Per-lane state.  A lane is busy exactly while it has a primitive group or a node group pending (a ray with
   // neither pops its stack or finishes in the same iteration), so there is no separate "active" flag.  CLASSIFY keeps
   // the winner's shade class in bits 28..30 of bPrim (the form the hit record has anyway).  A shadow ray's
@@ -234,43 +250,17 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           const float iay = __uint_as_float(((ew >> 8) & 0xffu) << 23) * idir.y;
           const float iaz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * idir.z;
           const float oax = (n0.x - o.x) * idir.x, oay = (n0.y - o.y) * idir.y, oaz = (n0.z - o.z) * idir.z;
-          // conservative: every axis gets its own rounding bound (2^-21 of the local origin term), folded
-          // into separate near / far addends so the per-child cost stays one FMA per plane; the far side
-          // is additionally widened by 1e-5 relative
-#if defined(MOX_BYTE_PRMT) || defined(MOX_BYTE_HYBRID)
-          const float kx = iax * 32768.f, ky = iay * 32768.f, kz = iaz * 32768.f;
-          const float ex_ = fmaf(2.384185791015625e-07f, fabsf(kx), 4.76837158203125e-07f * fabsf(oax));
-          const float ey_ = fmaf(2.384185791015625e-07f, fabsf(ky), 4.76837158203125e-07f * fabsf(oay));
-          const float ez_ = fmaf(2.384185791015625e-07f, fabsf(kz), 4.76837158203125e-07f * fabsf(oaz));
-          const float ofx = (oax + ex_) - kx, ofy = (oay + ey_) - ky, ofz = (oaz + ez_) - kz;
-#define MOX_FAR_SCALE_X kx
-#define MOX_FAR_SCALE_Y ky
-#define MOX_FAR_SCALE_Z kz
-#ifdef MOX_BYTE_PRMT
-          const float onx = (oax - ex_) - kx, ony = (oay - ey_) - ky, onz = (oaz - ez_) - kz;
-#define MOX_NEAR_SCALE_X kx
-#define MOX_NEAR_SCALE_Y ky
-#define MOX_NEAR_SCALE_Z kz
+          // conservative plane terms (planeTerms above); the far side is additionally widened by 1e-5 relative
+          constexpr unsigned MIX = MOX_BYTE_MIX;
+          float snx, onx, sfx, ofx, sny, ony, sfy, ofy, snz, onz, sfz, ofz;
+          planeTerms<(MIX & 1u) != 0, (MIX & 8u) != 0>(iax, oax, snx, onx, sfx, ofx);
+          planeTerms<(MIX & 2u) != 0, (MIX & 16u) != 0>(iay, oay, sny, ony, sfy, ofy);
+          planeTerms<(MIX & 4u) != 0, (MIX & 32u) != 0>(iaz, oaz, snz, onz, sfz, ofz);
+#if !defined(MOX_NODE_META) && MOX_HIT_SIGN
+          uint32_t hitmask = 0xff00ffffu;
 #else
-          const float onx = fmaf(-4.76837158203125e-07f, fabsf(oax), oax), ony = fmaf(-4.76837158203125e-07f, fabsf(oay), oay);
-          const float onz = fmaf(-4.76837158203125e-07f, fabsf(oaz), oaz);
-#define MOX_NEAR_SCALE_X iax
-#define MOX_NEAR_SCALE_Y iay
-#define MOX_NEAR_SCALE_Z iaz
-#endif
-#else
-          // (one FMA per addend: |oa| * 2^-21 is exact, so the sum is rounded once either way)
-          const float onx = fmaf(-4.76837158203125e-07f, fabsf(oax), oax), ofx = fmaf(4.76837158203125e-07f, fabsf(oax), oax);
-          const float ony = fmaf(-4.76837158203125e-07f, fabsf(oay), oay), ofy = fmaf(4.76837158203125e-07f, fabsf(oay), oay);
-          const float onz = fmaf(-4.76837158203125e-07f, fabsf(oaz), oaz), ofz = fmaf(4.76837158203125e-07f, fabsf(oaz), oaz);
-#define MOX_NEAR_SCALE_X iax
-#define MOX_NEAR_SCALE_Y iay
-#define MOX_NEAR_SCALE_Z iaz
-#define MOX_FAR_SCALE_X iax
-#define MOX_FAR_SCALE_Y iay
-#define MOX_FAR_SCALE_Z iaz
-#endif
           uint32_t hitmask = 0;
+#endif
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
 #ifdef MOX_NODE_META
@@ -289,16 +279,28 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
             const uint32_t nz = idir.z < 0.f ? qhz : qlz, fz = idir.z < 0.f ? qlz : qhz;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float tnx = fmaf(MOX_B2F_NEAR(nx, i), MOX_NEAR_SCALE_X, onx), tfx = fmaf(MOX_B2F_FAR(fx, i), MOX_FAR_SCALE_X, ofx);
-              const float tny = fmaf(MOX_B2F_NEAR(ny, i), MOX_NEAR_SCALE_Y, ony), tfy = fmaf(MOX_B2F_FAR(fy, i), MOX_FAR_SCALE_Y, ofy);
-              const float tnz = fmaf(MOX_B2F_NEAR(nz, i), MOX_NEAR_SCALE_Z, onz), tfz = fmaf(MOX_B2F_FAR(fz, i), MOX_FAR_SCALE_Z, ofz);
+              const float tnx = fmaf(byteToFloat<(MIX & 1u) != 0>(nx, i, one), snx, onx), tfx = fmaf(byteToFloat<(MIX & 8u) != 0>(fx, i, one), sfx, ofx);
+              const float tny = fmaf(byteToFloat<(MIX & 2u) != 0>(ny, i, one), sny, ony), tfy = fmaf(byteToFloat<(MIX & 16u) != 0>(fy, i, one), sfy, ofy);
+              const float tnz = fmaf(byteToFloat<(MIX & 4u) != 0>(nz, i, one), snz, onz), tfz = fmaf(byteToFloat<(MIX & 32u) != 0>(fz, i, one), sfz, ofz);
               const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+#if !defined(MOX_NODE_META) && MOX_HIT_SIGN
+              // hit <=> tf * 1.00001 - tn >= 0, read off the sign bit of one FMA (the FMA pipe has room, the ALU pipe
+              // that runs FSETP / SEL does not): every miss clears the child's constant from an all-hit mask
+              const float dd = fmaf(fminf(fminf(tfx, tfy), fminf(tfz, tBest)), 1.00001f, -tn);
+              const uint32_t K = (1u << (24 + 4 * half + i)) | (3u << (2 * (4 * half + i)));
+#if MOX_HIT_SIGN == 1
+              asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hitmask) : "r"(__float_as_uint(dd) >> 31), "r"(0u - K));
+#else
+              hitmask &= ~((uint32_t)(__float_as_int(dd) >> 31) & K);
+#endif
+#else
               const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tBest)) * 1.00001f;
+#endif
 #ifdef MOX_NODE_META
               // branch-free: an empty slot has count bits 0 (and an inverted box)
               const uint32_t bitsI = tn <= tf ? ((cnt4 >> (8 * i)) & 0xffu) : 0u;
               hitmask |= bitsI << ((pos4 >> (8 * i)) & 0xffu);
-#else
+#elif !MOX_HIT_SIGN
               // fixed positions per slot: one select of a compile-time constant per child (gpu_types.h)
               hitmask |= tn <= tf ? ((1u << (24 + 4 * half + i)) | (3u << (2 * (4 * half + i)))) : 0u;
 #endif
