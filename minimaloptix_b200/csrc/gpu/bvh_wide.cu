@@ -258,7 +258,7 @@ k_collapse_level(int nItems, const WorkItem* __restrict__ items, int nLeaves, co
 #ifdef MOX_NODE_META
   nd.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
 #else
-  nd.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float((imask << 24) | validPrims),
+  nd.n1 = make_float4(__uint_as_float(childBase), __uint_as_float(primBase), __uint_as_float((imask << MOX_NODE_VALID_INNER_SHIFT) | validPrims),
                       __uint_as_float((validPrims << 8) | imask));
 #endif
   nd.n2 = make_float4(__uint_as_float(pack4(qlx)), __uint_as_float(pack4(qlx + 4)), __uint_as_float(pack4(qly)), __uint_as_float(pack4(qly + 4)));

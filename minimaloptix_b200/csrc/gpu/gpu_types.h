@@ -72,6 +72,16 @@ static_assert(sizeof(BvhNode8) == 80, "BvhNode8");
 #ifndef MOX_WIDE_LEAF_MAX
 #define MOX_WIDE_LEAF_MAX 2  // measured: 2 -> 1037, 1 -> 1036, 3 -> 1013 Mrays/s (binary BVH: 1029)
 #endif
+// How the traversal turns a child's box test into hit bits (traverse_wide.cuh); form 3 accumulates the mask as a
+// float and wants the inner-child bits of the node's valid word at 16..23 instead of 24..31.
+#ifndef MOX_HIT_SIGN
+#define MOX_HIT_SIGN 1
+#endif
+#if MOX_HIT_SIGN == 3
+#define MOX_NODE_VALID_INNER_SHIFT 16
+#else
+#define MOX_NODE_VALID_INNER_SHIFT 24
+#endif
 #if !defined(MOX_NODE_META) && MOX_WIDE_LEAF_MAX > 2
 #error "the fixed-slot node layout has two primitive bits per slot: MOX_WIDE_LEAF_MAX > 2 needs MOX_NODE_META"
 #endif
