@@ -161,7 +161,8 @@ struct mox_ctx {
   bool disneySplit = false;      // Disney NORMAL shading as two kernels sharing a per-hit record (MOX_DISNEY_SPLIT=0: one kernel)
   bool brdfFast = true;          // approximate reciprocal / square root inside BRDF values (MOX_BRDF_IEEE=1: IEEE, the oracle's operations)
   bool hasDisneyNormal = false;  // some material runs the Disney NORMAL program (set by mox_build_accel)
-  bool sortRays = false;         // reorder the extend queue by (origin cell, direction octant) from bounce 2 on
+  bool sortRays = false;         // reorder the extend queue by (direction octant, origin cell) from bounce 2 on
+  int sortPasses = 3;            // 3: the whole 24-bit key; 1: octant + the 5 top bits of the cell (MOX_SORT_PASSES)
   float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {1, 1, 1};
 };
 
@@ -490,9 +491,9 @@ int sliceAdvance(mox_ctx* c, mox_ctx::Slice& sl) {
     bound = hostBounce[C_NEXT];
   }
   if (c->sortRays && bound > 4096) {
-    // 24-bit keys -> 3 passes: the sorted queue lands in (kBuf[1], qBuf[iSpare])
+    // 24-bit keys -> 3 passes (or their top 8 bits -> 1): the sorted queue lands in (kBuf[1], qBuf[iSpare])
     tm.begin(ST_SHADE, sl.stream);
-    radixSortAsync(pb.kBuf[0], pb.qBuf[sl.iNext], pb.kBuf[1], pb.qBuf[sl.iSpare], (int)bound, 3, pb.sortScratch, sl.stream);
+    radixSortAsync(pb.kBuf[0], pb.qBuf[sl.iNext], pb.kBuf[1], pb.qBuf[sl.iSpare], (int)bound, c->sortPasses, pb.sortScratch, sl.stream);
     tm.end(sl.stream);
     c->kernelLaunches += 5;
     int t = sl.iCur; sl.iCur = sl.iSpare; sl.iSpare = sl.iNext; sl.iNext = t;
@@ -569,6 +570,7 @@ int renderBatch(mox_ctx* c, const std::vector<int32_t>& seeds) {
     sl.iCur = 0; sl.iNext = 1; sl.iSpare = 2;
     lc.pb.qCur = pb.qBuf[sl.iCur]; lc.pb.qNext = pb.qBuf[sl.iNext];
     lc.pb.qKey = c->sortRays ? pb.kBuf[0] : nullptr;
+    lc.sortShift = c->sortPasses == 1 ? 16u : 0u;
     lc.bc = bounceBlock(pb, 1);
     sl.S = S; sl.bound = (uint32_t)paths; sl.depth = 1; sl.done = false; sl.applyPending = false;
     CUCK(c, cudaMemsetAsync(pb.counters, 0, kCounterWords * 4, sl.stream));
@@ -791,6 +793,7 @@ int mox_create(mox_ctx** out, int device_id) {
     return fail(nullptr, MOX_ERR_CUDA, msg);
   }
   if (const char* env = getenv("MOX_SORT_RAYS")) c->sortRays = atoi(env) != 0;
+  if (const char* env = getenv("MOX_SORT_PASSES")) c->sortPasses = atoi(env) == 1 ? 1 : 3;
   if (const char* env = getenv("MOX_MAX_BATCH_PATHS")) { long long v = atoll(env); if (v > 0) c->maxBatchPaths = (size_t)v; }
   if (const char* env = getenv("MOX_DISNEY_SPLIT")) c->disneySplit = atoi(env) != 0;
   if (const char* env = getenv("MOX_OVERLAP_SHADOW")) c->overlapShadow = atoi(env) != 0;

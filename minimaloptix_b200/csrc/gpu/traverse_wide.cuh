@@ -3,13 +3,14 @@
 // (t, id) lexicographic closest hit, order-independent shadow transmittance; only the hierarchy
 // walked differs, so results are bit-identical to the binary traversal.
 //
-// Per lane: a node group G = (childBase, hit bits 31..24 | imask 7..0) and a primitive group
-// T = (primBase, 24 hit bits), plus a stack of postponed node groups (Ylitie et al. 2017).  One
-// node step pops the front-most child of G (highest bit of slot ^ octant order), pushes the rest of
-// G, fetches the 80-byte node and tests its 8 quantised child boxes: one FMA per plane on a grid
-// local to the node, near/far planes picked per ray sign for four children at a time.  Warp phase
-// voting as in the binary kernel — a node step or one primitive test per iteration — but weighted by
-// cost (MOX_VOTE_TRI_WEIGHT): the cheaper primitive phase runs as soon as a quarter as many lanes want it.
+// Per lane: a node group G = (childBase, hit bits 31..24 | primitive bits that exist 23..8 | imask 7..0) and a
+// primitive group T = (primBase, 16 hit bits), plus a stack of postponed node groups (Ylitie et al. 2017).  One node
+// step pops the front-most child of G (highest bit of slot ^ octant order), pushes the rest of G, fetches the 80-byte
+// node and tests its 8 quantised child boxes: one FMA per plane on a grid local to the node, near/far planes picked
+// per ray sign for four children at a time, one more FMA + IMAD per child for its hit bits (fixed positions per slot,
+// gpu_types.h).  Warp phase voting as in the binary kernel — a node step or a primitive step (up to two primitives of
+// the lane) per iteration — but weighted by cost (MOX_VOTE_TRI_WEIGHT): the cheaper primitive phase runs as soon as a
+// third as many lanes want it.
 #pragma once
 #include "traverse.cuh"
 

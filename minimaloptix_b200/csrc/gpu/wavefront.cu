@@ -274,14 +274,14 @@ __device__ __forceinline__ void spawnAt(const LaunchCtx& c, uint32_t path, const
   c.pb.state[path] = childState;
   c.pb.qNext[pos] = path;
   if (c.pb.qKey) {
-    // reordering key: 21-bit Morton cell of the origin (7 bits/axis of the scene box) | direction octant
+    // reordering key: direction octant | 21-bit Morton cell of the origin (7 bits/axis of the scene box)
     uint32_t x = (uint32_t)fminf(fmaxf((o.x - c.sceneLo.x) * c.sceneInvExt.x, 0.f), 127.f);
     uint32_t y = (uint32_t)fminf(fmaxf((o.y - c.sceneLo.y) * c.sceneInvExt.y, 0.f), 127.f);
     uint32_t z = (uint32_t)fminf(fmaxf((o.z - c.sceneLo.z) * c.sceneInvExt.z, 0.f), 127.f);
     auto spread = [](uint32_t v) { v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
     uint32_t cell = (spread(x) << 2) | (spread(y) << 1) | spread(z);
     uint32_t oct = (d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u);
-    c.pb.qKey[pos] = (cell << 3) | oct;
+    c.pb.qKey[pos] = ((oct << 21) | cell) >> c.sortShift;   // octant on top: a one-pass sort keeps it
   }
 }
 __device__ __forceinline__ void spawn(const LaunchCtx& c, uint32_t path, const float3& o, const float3& d, const float3& A,

@@ -56,6 +56,7 @@ struct LaunchCtx {
   bool disneySplit;          // Disney NORMAL as two kernels (light sampling, then BSDF sampling) instead of one
   bool brdfFast;             // hardware reciprocal / square-root approximations inside BRDF values (shading.cuh::bdiv)
   float3 sceneLo, sceneInvExt;  // ray-reordering key: 7-bit cell of the origin inside the scene box
+  uint32_t sortShift = 0;       // the key's low bits dropped: 0 = 24-bit key (3 sort passes), 16 = octant + 5 cell bits (1 pass)
   cudaStream_t stream;
 };
 
