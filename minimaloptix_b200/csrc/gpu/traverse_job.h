@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define MOX_TRAV_TPB 128   // threads per CTA of the persistent traversal kernels
+#ifndef MOX_TRAV_TPB
+#define MOX_TRAV_TPB 128   // threads per CTA of the persistent traversal kernels (64 x 18 CTAs per SM and 256 x 4 measured: see DESIGN.md)
+#endif
 
 // One batch of rays for the persistent traversal kernel.
 //   rayO[id] = (origin, tmin)   rayD[id] = (direction, tmax); tmax < 0 marks an unused slot
