@@ -124,3 +124,111 @@ def test_prmt_byte_conversion_is_the_affine_map_within_the_stated_bound():
         far = f32(m * k + f32(f32(oa + e) - k))
         slack = 2.0 ** -23 * (abs(near) + abs(far)) + 1e-30  # the FMA's own rounding, covered by the 1e-5 far-side widening
         assert near <= exact + slack and far >= exact - slack
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The node test itself: quantisation as bvh_wide.cu::k_collapse_level does it, the plane arithmetic as
+# traverse_wide.cuh does it (float32, fused multiply-adds emulated through float64), against the exact slab test of the
+# child's true box in float64.  The traversal may visit too much, never too little: exact hit => kernel hit.
+def _fma(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def _grid_exponent(extent):
+    v = np.maximum(extent, np.float32(1e-30)) * np.float32(1.0 / 255.0)
+    _, k = np.frexp(v)
+    e = np.clip(k + 127, 1, 254)
+    for _ in range(3):   # guard against rounding in the division above
+        bump = (e < 254) & (np.float32(255.0) * np.ldexp(np.float32(1.0), e - 127).astype(np.float32) < extent)
+        e = e + bump
+    return e
+
+
+def _quantise(blo, s, lo, hi):
+    ql = np.clip(np.floor((lo - blo) / s), 0, 255).astype(np.int64)
+    qh = np.clip(np.ceil((hi - blo) / s), 0, 255).astype(np.int64)
+    for _ in range(3):   # outward rounding, verified against the planes the traversal will reconstruct
+        ql -= (ql > 0) & ((blo + ql.astype(np.float32) * s).astype(np.float32) > lo)
+        qh += (qh < 255) & ((blo + qh.astype(np.float32) * s).astype(np.float32) < hi)
+    return ql, qh
+
+
+@pytest.mark.parametrize("mix", [0x00, 0x33, 0x38, 0x3F])
+def test_quantised_box_test_is_conservative(mix):
+    rng = np.random.default_rng(1000 + mix)
+    n = 200000
+    f = np.float32
+    blo = (rng.normal(size=(n, 3)) * 50).astype(f)
+    ext = (10.0 ** rng.uniform(-3, 2, size=(n, 3))).astype(f)
+    ext[rng.random((n, 3)) < 0.05] = 0.0                                     # flat node boxes (walls, floors)
+    bhi = (blo + ext).astype(f)
+    ext = (bhi - blo).astype(f)
+    a, b = rng.random((n, 3)), rng.random((n, 3))
+    lo = (blo + np.minimum(a, b).astype(f) * ext).astype(f)
+    hi = (blo + np.maximum(a, b).astype(f) * ext).astype(f)
+    flat = rng.random((n, 3)) < 0.1
+    hi[flat] = lo[flat]                                                      # flat child boxes
+    lo, hi = np.clip(lo, blo, bhi), np.clip(hi, blo, bhi)
+    e = _grid_exponent(ext)
+    s = np.ldexp(f(1.0), e - 127).astype(f)
+    ql, qh = _quantise(blo, s, lo, hi)
+    assert np.all((blo + ql.astype(f) * s).astype(f) <= lo) and np.all((blo + qh.astype(f) * s).astype(f) >= hi)
+
+    # rays: aimed at a point of the child box (so that many of them hit), some axis-aligned, some far away
+    target = lo + rng.random((n, 3)).astype(f) * (hi - lo)
+    o = (target + rng.normal(size=(n, 3)).astype(f) * (10.0 ** rng.uniform(-2, 3, size=(n, 1))).astype(f)).astype(f)
+    d = (target - o).astype(np.float64)
+    d += rng.normal(size=(n, 3)) * 1e-3 * np.linalg.norm(d, axis=1, keepdims=True)   # graze: not all through the centre
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    d = d.astype(f)
+    axis_aligned = rng.random((n, 3)) < 0.02
+    d[axis_aligned] = 0.0
+    d[np.all(d == 0, axis=1)] = f(1.0)
+    tmin = f(1e-3)
+    tbest = np.where(rng.random(n) < 0.5, f(1e27), (10.0 ** rng.uniform(-2, 4, size=n)).astype(f)).astype(f)
+
+    # ---- exact slab test of the true child box (float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        o64, d64 = o.astype(np.float64), d.astype(np.float64)
+        t1, t2 = (lo - o64) / d64, (hi - o64) / d64
+        zero = d64 == 0
+        inside = (lo <= o64) & (o64 <= hi)
+        near = np.where(zero, np.where(inside, -np.inf, np.inf), np.minimum(t1, t2))   # a ray parallel to a slab is
+        far = np.where(zero, np.where(inside, np.inf, -np.inf), np.maximum(t1, t2))    # inside it for all t or for none
+    tn_true = np.maximum(near.max(axis=1), tmin)
+    tf_true = np.minimum(far.min(axis=1), tbest)
+    hit_true = tn_true <= tf_true
+
+    # ---- the kernel's arithmetic (float32)
+    dd = np.where(np.abs(d) > f(1e-30), d, np.copysign(f(1e-30), d)).astype(f)
+    idir = (f(1.0) / dd).astype(f)
+    ulp = rng.integers(-1, 2, size=idir.shape)                               # rcp.approx: 1 ulp
+    idir = np.where(ulp > 0, np.nextafter(idir, f(np.inf)), np.where(ulp < 0, np.nextafter(idir, f(-np.inf)), idir)).astype(f)
+    ia = (s * idir).astype(f)
+    oa = ((blo - o).astype(f) * idir).astype(f)
+    neg = idir < 0
+    nb, fb = np.where(neg, qh, ql), np.where(neg, ql, qh)
+    c21, c22 = f(4.76837158203125e-07), f(2.384185791015625e-07)
+    k = (ia * f(32768.0)).astype(f)
+    err = _fma(np.full_like(k, c22), np.abs(k), (c21 * np.abs(oa)).astype(f))
+    tn_ax, tf_ax = np.empty_like(oa), np.empty_like(oa)
+    for ax in range(3):
+        for far in (False, True):
+            byte = (fb if far else nb)[:, ax].astype(f)
+            if mix >> (ax + (3 if far else 0)) & 1:                          # PRMT form
+                m = (f(1.0) + byte * f(2.0 ** -15)).astype(f)
+                add = (((oa[:, ax] + err[:, ax]) if far else (oa[:, ax] - err[:, ax])).astype(f) - k[:, ax]).astype(f)
+                t = _fma(m, k[:, ax], add)
+            else:                                                            # I2F form
+                add = _fma(np.full(n, c21 if far else -c21, f), np.abs(oa[:, ax]), oa[:, ax])
+                t = _fma(byte, ia[:, ax], add)
+            (tf_ax if far else tn_ax)[:, ax] = t
+    tn = np.maximum(tn_ax.max(axis=1), tmin)
+    tf = np.minimum(tf_ax.min(axis=1), tbest)
+    diff = _fma(tf, np.full(n, f(1.00001)), -tn)                             # MOX_HIT_SIGN: the sign bit decides
+    hit_kernel = ~np.signbit(diff)
+    assert hit_true.sum() > n // 10                                          # the sample does exercise hits
+    missed = hit_true & ~hit_kernel
+    assert not missed.any(), f"{missed.sum()} exact hits culled, e.g. index {np.flatnonzero(missed)[:5]}"
+    # and it is a box test, not a constant: most exact misses stay misses
+    assert (hit_kernel & ~hit_true).sum() < 0.5 * (~hit_true).sum()
