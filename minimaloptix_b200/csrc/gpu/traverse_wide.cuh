@@ -16,6 +16,20 @@
 
 #define MOX_WIDE_STACK MOX_TRAVERSAL_STACK
 
+// Four small savings of the node / primitive step, adopted together at the very end of round 2 (1 662 -> 1 720 Mrays/s in
+// one A/B call, all GPU tests green on that library); MOX_NODE_STEP_R2A restores the forms measured until then:
+//   MOX_ADDEND_DIRECTED   PRMT-plane addends by directed rounding instead of an extra error bound (planeTerms)
+//   MOX_BFIND             highest set bit by FLO directly
+//   MOX_SWAP_PREDICATED   the octant swaps predicated on the signs of 1/d the node step tests anyway
+//   MOX_ONE_FMA           the 1.0f pattern of the PRMT conversion from one FMA
+#ifndef MOX_NODE_STEP_R2A
+#define MOX_ADDEND_DIRECTED
+#define MOX_BFIND
+#define MOX_SWAP_PREDICATED
+#define MOX_ONE_FMA
+#endif
+
+
 // Quantised plane byte -> float, two ways, mixed per plane so that neither pipe is the bottleneck:
 //  * I2F.U8 on the conversion pipe (15.4 results/clk/SM measured, scripts/microbench/pipe_rates.cu, against 124
 //    FFMA): with all 48 conversions of a node step on it that pipe was ~70 % busy and 15-19 % of the stall samples
@@ -62,10 +76,28 @@ MOX_D float byteToFloat(uint32_t w, int i, uint32_t one) {
 template <bool NEAR_PRMT, bool FAR_PRMT>
 MOX_D void planeTerms(float ia, float oa, float& sn, float& an, float& sf, float& af) {
   const float k = ia * 32768.f;
-  const float e = fmaf(2.384185791015625e-07f, fabsf(k), 4.76837158203125e-07f * fabsf(oa));
   // (I2F form: |oa| * 2^-21 is exact, so one FMA rounds the same sum once)
-  if (NEAR_PRMT) { sn = k; an = (oa - e) - k; } else { sn = ia; an = fmaf(-4.76837158203125e-07f, fabsf(oa), oa); }
-  if (FAR_PRMT) { sf = k; af = (oa + e) - k; } else { sf = ia; af = fmaf(4.76837158203125e-07f, fabsf(oa), oa); }
+  const float an0 = fmaf(-4.76837158203125e-07f, fabsf(oa), oa), af0 = fmaf(4.76837158203125e-07f, fabsf(oa), oa);
+#ifdef MOX_ADDEND_DIRECTED
+  // PRMT form: the only new rounding is the subtraction of 2^15 ia from the addend — rounded towards the outside of the
+  // box (FADD.RM / FADD.RP) it needs no bound of its own: two instructions per plane instead of four
+  if (NEAR_PRMT) { sn = k; an = __fsub_rd(an0, k); } else { sn = ia; an = an0; }
+  if (FAR_PRMT) { sf = k; af = __fsub_ru(af0, k); } else { sf = ia; af = af0; }
+#else
+  const float e = fmaf(2.384185791015625e-07f, fabsf(k), 4.76837158203125e-07f * fabsf(oa));
+  if (NEAR_PRMT) { sn = k; an = (oa - e) - k; } else { sn = ia; an = an0; }
+  if (FAR_PRMT) { sf = k; af = (oa + e) - k; } else { sf = ia; af = af0; }
+#endif
+}
+// index of the highest set bit (x != 0): FLO directly — written as 31 - __clz(x), ptxas keeps both subtractions
+MOX_D uint32_t highestBit(uint32_t x) {
+#ifdef MOX_BFIND
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+#else
+  return 31u - (uint32_t)__clz(x);
+#endif
 }
 
 // (a & m) | (b & ~m) as one LOP3 (written as two ANDs and an OR, ptxas spends two)
@@ -97,7 +129,9 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
   }
 #endif
   // 0x3f800000 that ptxas cannot fold into an immediate (a launch never has 2^31 rays)
+#ifndef MOX_ONE_FMA
   const uint32_t one = 0x3f800000u | (job.count >> 31);
+#endif
   // Per-lane state.  A lane is busy exactly while it has a primitive group or a node group pending (a ray with
   // neither pops its stack or finishes in the same iteration), so there is no separate "active" flag.  CLASSIFY keeps
   // the winner's shade class in bits 28..30 of bPrim (the form the hit record has anyway).  A shadow ray's
@@ -172,7 +206,11 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
             RayPre r = prepRay(mk3(ro), mk3(rd), ro.w);
             o = r.o; d = r.d; idir = r.idir; tmin = r.tmin;
             if (WT) wr = wtPrep(d);
+#ifdef MOX_SWAP_PREDICATED
+            octinv = 7u ^ ((idir.x < 0.f ? 4u : 0u) | (idir.y < 0.f ? 2u : 0u) | (idir.z < 0.f ? 1u : 0u));   // (-0.0 counts as negative here)
+#else
             octinv = 7u ^ ((d.x < 0.f ? 4u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 1u : 0u));
+#endif
             tBest = rd.w; bPrim = -1;
             if (!CLASSIFY) { bBeta = 0.f; bGamma = 0.f; }
             tinted = false;
@@ -226,7 +264,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
 #endif
         if (isNode) {
           // ---- pop the front-most pending child of G
-          const uint32_t bit = 31u - (uint32_t)__clz(gBits & 0xff000000u);
+          const uint32_t bit = highestBit(gBits & 0xff000000u);
           const uint32_t imaskG = gBits & 0xffu;
           gBits &= ~(1u << bit);
           const uint32_t slot = (bit - 24u) ^ octinv;
@@ -252,6 +290,11 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           const float iay = __uint_as_float(((ew >> 8) & 0xffu) << 23) * idir.y;
           const float iaz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * idir.z;
           const float oax = (n0.x - o.x) * idir.x, oay = (n0.y - o.y) * idir.y, oaz = (n0.z - o.z) * idir.z;
+#ifdef MOX_ONE_FMA
+          // ... or one FMA per node step (0 * finite + 1; neither nvcc nor ptxas may fold it) instead of a constant
+          // load and an ALU instruction to rebuild the value ptxas does not keep in a register across the loop
+          const uint32_t one = __float_as_uint(fmaf(0.f, idir.x, 1.0f));
+#endif
           // conservative plane terms (planeTerms above); the far side is additionally widened by 1e-5 relative
           constexpr unsigned MIX = MOX_BYTE_MIX;
           float snx, onx, sfx, ofx, sny, ony, sfy, ofy, snz, onz, sfz, ofz;
@@ -333,11 +376,19 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
           tBits = hitmask & 0x0000ffffu;
 #endif
           {
-            const uint32_t s4 = octinv & 4u, s2 = octinv & 2u, s1 = octinv & 1u;
             uint32_t x = hitmask;
+#ifdef MOX_SWAP_PREDICATED
+            // the octant mask is made of the signs of 1/d (see the refill), the predicates the near/far selects of this
+            // node step hold anyway: three predicated instructions per swap
+            if (!(idir.x < 0.f)) x = bitSelect(x << 4, x >> 4, 0xf0000000u);
+            if (!(idir.y < 0.f)) x = bitSelect(x << 2, x >> 2, 0xcc000000u);
+            if (!(idir.z < 0.f)) x = bitSelect(x << 1, x >> 1, 0xaa000000u);
+#else
+            const uint32_t s4 = octinv & 4u, s2 = octinv & 2u, s1 = octinv & 1u;
             x = bitSelect(x << s4, x >> s4, 0xf0000000u);
             x = bitSelect(x << s2, x >> s2, 0xcc000000u);
             x = bitSelect(x << s1, x >> s1, 0xaa000000u);
+#endif
             gBits = (x & 0xff000000u) | __float_as_uint(n1.w);   // n1.w = V << 8 | imask
           }
 #endif
@@ -416,11 +467,11 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
         };
 #if MOX_PRIMS_PER_STEP == 2 && defined(MOX_PRIM_PREFETCH)
         if (isTri) {
-          const uint32_t k1 = 31u - (uint32_t)__clz(tBits);
+          const uint32_t k1 = highestBit(tBits);
           const float4* recA = recordOf(k1);
           tBits &= ~(1u << k1);
           const bool two = tBits != 0u;
-          const uint32_t k2 = two ? 31u - (uint32_t)__clz(tBits) : k1;
+          const uint32_t k2 = two ? highestBit(tBits) : k1;
           const float4* recB = recordOf(k2);
           tBits &= ~(1u << k2);
           // All words are fetched before a type is known (see below)
@@ -433,7 +484,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
 #pragma unroll
         for (int rep = 0; rep < MOX_PRIMS_PER_STEP; ++rep)
         if (rep == 0 ? isTri : tBits != 0u) {
-          const uint32_t k = 31u - (uint32_t)__clz(tBits);
+          const uint32_t k = highestBit(tBits);
           const float4* rec = recordOf(k);
           tBits &= ~(1u << k);
           // All three words are fetched before the type is known: the tag is folded from words 0 and 2 and the

@@ -153,8 +153,17 @@ def _quantise(blo, s, lo, hi):
     return ql, qh
 
 
+def _round_directed(x64, up):
+    """float64 -> float32 rounded towards +inf (up) or -inf, as FADD.RP / FADD.RM do."""
+    r = x64.astype(np.float32)
+    if up:
+        return np.where(r.astype(np.float64) < x64, np.nextafter(r, np.float32(np.inf)), r).astype(np.float32)
+    return np.where(r.astype(np.float64) > x64, np.nextafter(r, np.float32(-np.inf)), r).astype(np.float32)
+
+
+@pytest.mark.parametrize("directed", [False, True], ids=["bounded", "directed"])
 @pytest.mark.parametrize("mix", [0x00, 0x33, 0x38, 0x3F])
-def test_quantised_box_test_is_conservative(mix):
+def test_quantised_box_test_is_conservative(mix, directed):
     rng = np.random.default_rng(1000 + mix)
     n = 200000
     f = np.float32
@@ -217,7 +226,11 @@ def test_quantised_box_test_is_conservative(mix):
             byte = (fb if far else nb)[:, ax].astype(f)
             if mix >> (ax + (3 if far else 0)) & 1:                          # PRMT form
                 m = (f(1.0) + byte * f(2.0 ** -15)).astype(f)
-                add = (((oa[:, ax] + err[:, ax]) if far else (oa[:, ax] - err[:, ax])).astype(f) - k[:, ax]).astype(f)
+                if directed:   # MOX_ADDEND_DIRECTED: the I2F addend minus 2^15 ia, rounded away from the box
+                    add0 = _fma(np.full(n, c21 if far else -c21, f), np.abs(oa[:, ax]), oa[:, ax])
+                    add = _round_directed(add0.astype(np.float64) - k[:, ax].astype(np.float64), up=far)
+                else:
+                    add = (((oa[:, ax] + err[:, ax]) if far else (oa[:, ax] - err[:, ax])).astype(f) - k[:, ax]).astype(f)
                 t = _fma(m, k[:, ax], add)
             else:                                                            # I2F form
                 add = _fma(np.full(n, c21 if far else -c21, f), np.abs(oa[:, ax]), oa[:, ax])
