@@ -246,7 +246,7 @@ __device__ __forceinline__ void traverseWidePersistent(const SceneView& s, const
       const bool isTri = tBits != 0u;
       const bool isNode = !isTri && (gBits & 0xff000000u) != 0u;
 #ifndef MOX_VOTE_TRI_WEIGHT
-#define MOX_VOTE_TRI_WEIGHT 3  // a primitive step costs less than half a node step: vote by cost, not by head count (measured 1: 1115, 2: 1191, 3: 1206, 4: 1214, 6: 1207, 32: 1069 Mrays/s)
+#define MOX_VOTE_TRI_WEIGHT 3  // a primitive step costs less than half a node step: vote by cost, not by head count (round 1: 1: 1115, 2: 1191, 3: 1206, 4: 1214, 6: 1207, 32: 1069 Mrays/s; with the cheaper node step of round 2 and two primitives per step: 2: 1693-1696, 3: 1691-1692, 4: 1671)
 #endif
 #ifndef MOX_VOTE_POPC
       // one ballot + one warp reduction (REDUX) of the weighted vote instead of two ballots + two POPCs — POPC shares the
