@@ -376,9 +376,10 @@ bool readImageRgba(const std::string& path, int& w, int& h, std::vector<float>& 
     int ch = f[1] == 'F' ? 3 : 1;  // PFM: rows bottom-up already, little-endian when scale < 0
     if (vals[2] >= 0 || pos + (size_t)w * h * ch * 4 > f.size()) { err = "unsupported PFM (need little-endian)"; return false; }
     texels.resize((size_t)w * h * 4);
-    const float* src = (const float*)&f[pos];
+    const uint8_t* src = &f[pos];   // not 4-byte aligned in general: the header has any length
+    auto at = [&](size_t k) { float v; memcpy(&v, src + 4 * k, 4); return v; };
     for (size_t i = 0; i < (size_t)w * h; ++i) {
-      float r = src[i * ch], g = ch == 3 ? src[i * ch + 1] : r, b = ch == 3 ? src[i * ch + 2] : r;
+      float r = at(i * ch), g = ch == 3 ? at(i * ch + 1) : r, b = ch == 3 ? at(i * ch + 2) : r;
       texels[4 * i] = r; texels[4 * i + 1] = g; texels[4 * i + 2] = b; texels[4 * i + 3] = 1.f;
     }
     return true;

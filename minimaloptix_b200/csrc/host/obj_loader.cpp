@@ -197,7 +197,7 @@ bool tryParseDouble(const char* s, const char* s_end, double* result) {
     nread = 0;
     more = c != s_end;
     while (more && isDigit(*c)) {
-      expo = expo * 10 + (int)(*c - '0');
+      if (expo < 100000) expo = expo * 10 + (int)(*c - '0');   // saturate: tinyobj's int overflows (UB) on "1e9999999999"; the value is inf or 0 either way
       ++c; ++nread;
       more = c != s_end;
     }
